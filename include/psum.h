@@ -1,0 +1,142 @@
+/* psum.h -- C ABI of libpsum.so: the B200-native Pauli-sum H.psi / <psi|H|psi> engine.
+ *
+ * The reference (qiskit-aqua 0.10.0) is pure Python and has NO native interface for this path
+ * (its setup.py:38-76 declares no extension modules), so there is no existing FFI to match.
+ * Each entry point below names the reference function whose arithmetic it replaces; the Python
+ * shim in qiskit_aqua_b200/ binds them with ctypes (INTEGRATION.md shows the stub a maintainer
+ * would add on the reference side).
+ *
+ * Conventions
+ *   - n qubits, N = 2^n amplitudes, qubit q <-> bit q of the basis index.
+ *   - a term k is (x_mask, z_mask, ypow, coeff):  P_k[i, i^x] = (-i)^ypow (-1)^popc(i & z)
+ *     with ypow = popc(x & z) mod 4 for a label Pauli (terra Pauli.to_matrix convention).
+ *   - state vectors are complex128 (interleaved re,im doubles), DEVICE pointers, 16-byte aligned.
+ *   - every function returns PSUM_OK (0) or a negative code; psum_last_error() gives the text
+ *     (thread-local).  No exceptions/aborts cross the ABI.  There is NO CPU fallback: compute
+ *     entry points fail with PSUM_ERR_CUDA when no device is usable.
+ *   - a handle is not thread-safe; calls are ordered on the given stream; calls that return a
+ *     scalar to the host synchronise that stream.
+ */
+#ifndef PSUM_H
+#define PSUM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psum_handle_s* psum_handle_t;
+typedef void* psum_stream_t; /* cudaStream_t */
+
+#define PSUM_OK 0
+#define PSUM_ERR_INVALID (-1)
+#define PSUM_ERR_CUDA (-2)
+#define PSUM_ERR_EMPTY (-3)          /* reference: AquaError("Operator is empty") weighted_pauli_operator.py:616 */
+#define PSUM_ERR_NOT_HERMITIAN (-4)  /* Lanczos needs real label coefficients */
+#define PSUM_ERR_NOT_DIAGONAL (-5)
+#define PSUM_ERR_NCCL (-6)
+#define PSUM_ERR_NOMEM (-7)
+#define PSUM_ERR_NOT_CONVERGED (-8)
+
+const char* psum_last_error(void);
+int psum_version(void);
+
+/* ---- operator handle ------------------------------------------------------------------ */
+/* Pack step.  Replaces WeightedPauliOperator.__init__/simplify
+ * (legacy/weighted_pauli_operator.py:43-70, 341-400): duplicate (x,z) are merged, exact zeros
+ * dropped; and op_converter.to_matrix_operator (legacy/op_converter.py:103-124) in the sense that
+ * no matrix is ever built.  Host-only work; the device copy of the plan is made on first use. */
+int psum_create(int n_qubits, int64_t n_terms, const uint64_t* x_mask, const uint64_t* z_mask,
+                const uint8_t* ypow, const double* coeff_re_im, psum_handle_t* out);
+int psum_destroy(psum_handle_t h);
+
+/* Tuning/testing knobs (before first use): "tile_bits" (8..13), "low_bits" (1..6),
+ * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover". */
+int psum_set_option(psum_handle_t h, const char* key, int64_t value);
+
+/* info[0]=n_qubits [1]=merged terms [2]=distinct x-masks (G_x) [3]=passes [4]=groups read from
+ * global memory ("remote") [5]=is_hermitian [6]=is_diagonal [7]=local qubits [8]=sum of patterns
+ * [9]=component terms [10]=tile_bits [11]=distinct non-zero global x-parts */
+int psum_info(psum_handle_t h, int64_t* info, int n_info);
+/* Free-bit set (bit mask over local qubits) and group count of pass p of global part g. */
+int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* n_groups,
+                   int64_t* n_remote_groups, int64_t* n_patterns);
+
+/* ---- H.psi and <psi|H|psi> ------------------------------------------------------------ */
+/* y = H psi ; if expect_out != NULL also expect_out = {Re,Im} of sum_i conj(psi_i) y_i (host
+ * pointer, forces a stream sync).  Replaces `mat_op._matrix.dot(psi)` (+ np.vdot) at
+ * legacy/weighted_pauli_operator.py:621-622 and MatrixOp.eval primitive_ops/matrix_op.py:207. */
+int psum_apply(psum_handle_t h, const void* psi_dev, void* y_dev, double* expect_out,
+               psum_stream_t stream);
+/* <psi|H|psi> without storing y.  Replaces evaluate_with_statevector
+ * (legacy/weighted_pauli_operator.py:605-623), OperatorStateFn.eval
+ * (state_fns/operator_state_fn.py:179-208) and _eval_aux_operators
+ * (algorithms/eigen_solvers/numpy_eigen_solver.py:208-226). */
+int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], psum_stream_t stream);
+/* <phi|H|psi> for a different bra (ListOp / transition elements). */
+int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, double out[2],
+                   psum_stream_t stream);
+/* The same for `batch` state vectors stored back to back (VQE max_evals_grouped batching,
+ * vqe.py:518, matrix_op.py:199-201).  out = 2*batch doubles on the host. */
+int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev, double* out,
+                      psum_stream_t stream);
+
+/* ---- diagonal (all-Z) operators: numpy_eigen_solver.py:163-169 ------------------------ */
+/* d_dev[i] = Re sum_k c_k (-1)^popc(i & z_k) as float64[N] on the device. */
+int psum_diag(psum_handle_t h, double* d_dev, psum_stream_t stream);
+/* k smallest diagonal entries, ascending, ties broken by lower index (np.sort / np.argsort). */
+int psum_diag_kmin(psum_handle_t h, int k, double* vals, uint64_t* idx, psum_stream_t stream);
+
+/* ---- eigensolver: replaces scipy eigs(H_csr, k, which='SR') numpy_eigen_solver.py:175-176 */
+/* Device-resident Lanczos (full re-orthogonalisation while the basis fits in `mem_budget_bytes`
+ * of device memory, otherwise 3-vector recurrence + a second pass for the vectors).
+ * evals: k doubles (ascending).  evecs_dev: k*N complex128 on the device or NULL.
+ * resid_out: k residual norms |H v - lambda v| or NULL.  Returns PSUM_ERR_NOT_HERMITIAN for
+ * complex label coefficients. */
+int psum_lanczos(psum_handle_t h, int k, double tol, int max_iter, uint64_t seed,
+                 int64_t mem_budget_bytes, double* evals, void* evecs_dev, double* resid_out,
+                 int* iters_out, psum_stream_t stream);
+
+/* ---- vector helpers used by the host-side callers (device pointers, complex128) -------- */
+/* Counter-based synthetic state: psi[i] = gauss(seed, first_index + i); its CPU twin is
+ * oracle/psum_oracle.c:psum_oracle_state.  Not normalised. */
+int psum_fill_state(void* psi_dev, uint64_t n_amps, uint64_t first_index, uint64_t seed,
+                    psum_stream_t stream);
+int psum_vec_dot(const void* a_dev, const void* b_dev, uint64_t n_amps, double out[2],
+                 psum_stream_t stream);          /* sum conj(a) b */
+int psum_vec_scale(void* a_dev, uint64_t n_amps, double s_re, double s_im, psum_stream_t stream);
+int psum_vec_axpy(void* y_dev, const void* x_dev, uint64_t n_amps, double a_re, double a_im,
+                  psum_stream_t stream);         /* y += a x */
+
+/* ---- sharding over the top log2(world) qubits (one process per GPU) -------------------- */
+/* 128-byte NCCL unique id (rank 0 creates it; the host broadcasts it, e.g. torch.distributed). */
+int psum_nccl_unique_id(void* out128);
+/* Re-plans the handle for this rank's shard.  unique_id128 == NULL -> no communicator is made
+ * (plan inspection / CPU-side tests / caller-driven exchange through psum_apply_part). */
+int psum_shard_init(psum_handle_t h, int rank, int world, const void* unique_id128);
+/* Contribution of the terms whose global x-part is g (0 <= g < world) to this rank's y, reading
+ * partner amplitudes from src_dev (= the shard of rank r^g; g == 0 -> the local shard).
+ * accumulate != 0 adds into y_dev.  expect_acc (host, 2 doubles, may be NULL) += sum conj(bra) y
+ * with bra_dev = this rank's own shard. */
+int psum_apply_part(psum_handle_t h, int g, const void* src_dev, const void* bra_dev, void* y_dev,
+                    int accumulate, double* expect_acc, psum_stream_t stream);
+/* Component terms this rank applies for global part g (rank sign folded in): for CPU-side
+ * checks of the sharding algebra.  Arrays of capacity cap; returns the count in *n_out. */
+int psum_shard_terms(psum_handle_t h, int g, int64_t cap, uint64_t* x_local, uint64_t* z_local,
+                     double* coeff_re_im, int64_t* n_out);
+/* Sharded H.psi with the NCCL amplitude exchange inside (needs psum_shard_init with an id):
+ * recv_dev is a caller-provided exchange buffer of recv_amps >= N_loc amplitudes (may be NULL
+ * when no term has a global x-part); with >= 2 N_loc the exchange of part g+1 overlaps the
+ * passes over part g.  y_dev may be NULL (expectation only).  expect_out (may be NULL) receives
+ * the all-reduced <psi|H|psi>. */
+int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
+                       uint64_t recv_amps, double* expect_out, psum_stream_t stream);
+/* Host-side eigen-solver test hook (no device): which = 0 dense Jacobi (A = n*n), 1 tridiagonal
+ * QL (A = d[n], e[n]).  w[n] ascending, V n*n eigenvectors in columns (may be NULL). */
+int psum_test_eigh(int which, int n, const double* A, double* w, double* V);
+int psum_allreduce_sum(psum_handle_t h, double* host_vals, int n); /* small host scalars */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSUM_H */

@@ -1,0 +1,9 @@
+"""qiskit_aqua_b200 -- B200-native drop-in for Aqua's Pauli-sum H.psi / <psi|H|psi> hot path.
+
+Only the one hot path of qiskit-aqua 0.10.0 is provided; the compute runs in
+hand-written sm_100a CUDA kernels behind the C ABI in include/psum.h (libpsum.so).
+"""
+from ._lib import PsumError, lib  # noqa: F401
+from .engine import PauliSumEngine, fill_state, nccl_unique_id, pack_masks  # noqa: F401
+
+__version__ = '0.1.0'

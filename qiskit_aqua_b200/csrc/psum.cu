@@ -1,0 +1,780 @@
+// psum.cu -- C ABI (include/psum.h) over the sm_100a kernels in psum_kernels.cuh.
+// Host logic: handle, plan upload, launch sequencing, NCCL amplitude exchange, Lanczos driver.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/psum.h"
+#include "psum_eig.h"
+#include "psum_kernels.cuh"
+#include "psum_plan.h"
+
+using namespace psum;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(PSUM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+#define PS_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != PSUM_OK) return _r; \
+  } while (0)
+
+extern "C" const char* psum_last_error(void) { return g_err; }
+extern "C" int psum_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen (only touched by the sharded entry points)
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;
+
+int load_nccl() {
+  if (g_nccl.lib) return PSUM_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* nm : names) {
+    lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(PSUM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LOAD(sym)                                                              \
+  *(void**)(&g_nccl.sym) = dlsym(lib, "nccl" #sym);                             \
+  if (!g_nccl.sym) return fail(PSUM_ERR_NCCL, "libnccl lacks symbol nccl" #sym);
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(AllReduce)
+  LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+  g_nccl.lib = lib;
+  return PSUM_OK;
+}
+#define NCCL_TRY(expr)                                                                        \
+  do {                                                                                        \
+    int _r = (expr);                                                                          \
+    if (_r != 0) return fail(PSUM_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(_r)); \
+  } while (0)
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct DevPass {
+  PassParams params;
+  int grid = 0;
+  size_t smem = 0;
+};
+struct DevPart {
+  int g = 0;
+  std::vector<DevPass> passes;
+  SimpleGroup* sgroups = nullptr;
+  SimpleTerm* sterms = nullptr;
+  int nsg = 0, nst = 0;
+  int grid_stream = 0;
+};
+
+struct psum_handle_s {
+  int n = 0, p_bits = 0, rank = 0, world = 1, n_loc = 0;
+  std::vector<MergedTerm> terms;
+  bool hermitian = true, diagonal = true;
+  PlanOptions opt;
+  std::vector<PartHost> parts;
+  bool planned = false;
+  // device side
+  bool uploaded = false;
+  int device = -1, num_sms = 0;
+  void* arena = nullptr;
+  std::vector<DevPart> dparts;
+  double2* d_partial = nullptr;
+  size_t partial_cap = 0;
+  double2* d_scalar = nullptr;  // 64 complex scalars
+  double2* h_scalar = nullptr;  // pinned mirror
+  // sharding
+  nccl_comm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_recv[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+};
+
+static uint64_t n_local_amps(const psum_handle_s* h) { return 1ull << h->n_loc; }
+
+static void free_device(psum_handle_s* h) {
+  if (h->arena) cudaFree(h->arena);
+  if (h->d_partial) cudaFree(h->d_partial);
+  if (h->d_scalar) cudaFree(h->d_scalar);
+  if (h->h_scalar) cudaFreeHost(h->h_scalar);
+  h->arena = nullptr;
+  h->d_partial = nullptr;
+  h->d_scalar = nullptr;
+  h->h_scalar = nullptr;
+  h->dparts.clear();
+  h->uploaded = false;
+}
+
+static int plan(psum_handle_s* h) {
+  h->parts = build_parts(h->terms, h->n, h->p_bits, h->rank, h->opt);
+  h->planned = true;
+  if (h->uploaded) free_device(h);
+  return PSUM_OK;
+}
+
+static size_t pass_smem_bytes(int L) {
+  return ((size_t)16 << L) + 8 * kPatChunk + 8 * 32 + sizeof(GroupRec) * kGrpChunk + 2 * kPatChunk +
+         16 * (kThreads / 32);
+}
+
+template <typename T>
+static T* arena_put(char* base, size_t& off, const std::vector<T>& v, std::vector<char>& host) {
+  off = (off + 255) & ~(size_t)255;
+  size_t bytes = v.size() * sizeof(T);
+  if (host.size() < off + bytes) host.resize(off + bytes);
+  if (bytes) memcpy(host.data() + off, v.data(), bytes);
+  T* p = reinterpret_cast<T*>(base + off);
+  off += bytes;
+  return p;
+}
+
+static int upload(psum_handle_s* h) {
+  if (h->uploaded) return PSUM_OK;
+  if (!h->planned) PS_TRY(plan(h));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PSUM_ERR_CUDA, "no CUDA device available (%s); libpsum has no CPU fallback",
+                cudaGetErrorString(e));
+  CUDA_TRY(cudaGetDevice(&h->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  // two-phase arena: first size, then fill
+  std::vector<char> host;
+  size_t off = 0;
+  // phase 1 to compute offsets with a null base
+  h->dparts.clear();
+  size_t max_partials = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    char* base = (char*)h->arena;
+    off = 0;
+    host.clear();
+    h->dparts.clear();
+    max_partials = 0;
+    for (const PartHost& P : h->parts) {
+      DevPart D;
+      D.g = P.g;
+      D.sgroups = arena_put(base, off, P.sgroups, host);
+      D.sterms = arena_put(base, off, P.sterms, host);
+      D.nsg = (int)P.sgroups.size();
+      D.nst = (int)P.sterms.size();
+      uint64_t blocks = (n_local_amps(h) + kThreads - 1) / kThreads;
+      D.grid_stream = (int)std::min<uint64_t>(blocks, (uint64_t)h->num_sms * 8);
+      size_t partials = D.grid_stream;
+      size_t pass_partials = 0;
+      for (const PassHost& ph : P.passes) {
+        DevPass dp;
+        memset(&dp.params, 0, sizeof(dp.params));
+        dp.params.groups = arena_put(base, off, ph.groups, host);
+        dp.params.pat_zt = arena_put(base, off, ph.pat_zt, host);
+        dp.params.pat_tptr = arena_put(base, off, ph.pat_tptr, host);
+        dp.params.term_zb = arena_put(base, off, ph.term_zb, host);
+        dp.params.term_val = arena_put(base, off, ph.term_val, host);
+        dp.params.chunks = arena_put(base, off, ph.chunks, host);
+        dp.params.nchunks = (int)ph.chunks.size();
+        dp.params.L = ph.L;
+        dp.params.n_nonfree = h->n_loc - ph.L;
+        dp.params.ntiles = 1ull << (h->n_loc - ph.L);
+        int fj = 0, nj = 0;
+        for (int b = 0; b < h->n_loc; ++b) {
+          if (ph.free_mask >> b & 1ull) dp.params.fbit[fj++] = (uint8_t)b;
+          else dp.params.nbit[nj++] = (uint8_t)b;
+        }
+        dp.smem = pass_smem_bytes(ph.L);
+        int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
+        dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
+        pass_partials += dp.grid;
+        D.passes.push_back(dp);
+      }
+      partials = std::max(partials, pass_partials);
+      max_partials += partials;
+      h->dparts.push_back(std::move(D));
+    }
+    if (phase == 0) {
+      size_t bytes = std::max<size_t>(off, 256);
+      CUDA_TRY(cudaMalloc(&h->arena, bytes));
+    } else if (off) {
+      CUDA_TRY(cudaMemcpy(h->arena, host.data(), off, cudaMemcpyHostToDevice));
+    }
+  }
+  h->partial_cap = std::max<size_t>(max_partials, 4096) * 2 + 64 * 4096;
+  CUDA_TRY(cudaMalloc(&h->d_partial, h->partial_cap * sizeof(double2)));
+  CUDA_TRY(cudaMalloc(&h->d_scalar, 256 * sizeof(double2)));
+  CUDA_TRY(cudaMallocHost(&h->h_scalar, 256 * sizeof(double2)));
+  static bool attr_done = false;
+  if (!attr_done) {
+    int max_smem = (int)pass_smem_bytes(kMaxTileBits);
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_done = true;
+  }
+  h->uploaded = true;
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create / destroy / info
+// ---------------------------------------------------------------------------------------------
+extern "C" int psum_create(int n_qubits, int64_t n_terms, const uint64_t* x_mask,
+                           const uint64_t* z_mask, const uint8_t* ypow, const double* coeff_re_im,
+                           psum_handle_t* out) {
+  if (!out) return fail(PSUM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_qubits < 1 || n_qubits > 64) return fail(PSUM_ERR_INVALID, "n_qubits=%d out of [1,64]", n_qubits);
+  if (n_terms < 0 || (n_terms > 0 && (!x_mask || !z_mask || !coeff_re_im)))
+    return fail(PSUM_ERR_INVALID, "bad term arrays");
+  const uint64_t lm = low_mask(n_qubits);
+  for (int64_t k = 0; k < n_terms; ++k)
+    if ((x_mask[k] & ~lm) || (z_mask[k] & ~lm))
+      return fail(PSUM_ERR_INVALID, "term %lld has mask bits above qubit %d", (long long)k, n_qubits - 1);
+  psum_handle_s* h = new psum_handle_s();
+  h->n = h->n_loc = n_qubits;
+  h->terms = merge_terms(n_terms, x_mask, z_mask, ypow, coeff_re_im);
+  double cmax = 0.0;
+  for (auto& t : h->terms) cmax = std::max(cmax, std::max(fabs(t.re), fabs(t.im)));
+  for (auto& t : h->terms) {
+    if (t.x) h->diagonal = false;
+    // coefficient of the Hermitian label Pauli = c' * i^{nY}
+    int ny = popc64(t.x & t.z) & 3;
+    double im = (ny == 0) ? t.im : (ny == 1) ? t.re : (ny == 2) ? -t.im : -t.re;
+    if (fabs(im) > 1e-13 * cmax) h->hermitian = false;
+  }
+  *out = h;
+  return PSUM_OK;
+}
+
+extern "C" int psum_destroy(psum_handle_t h) {
+  if (!h) return PSUM_OK;
+  free_device(h);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_recv[i]) cudaEventDestroy(h->ev_recv[i]);
+    if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
+  }
+  delete h;
+  return PSUM_OK;
+}
+
+extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) {
+  if (!h || !key) return fail(PSUM_ERR_INVALID, "null argument");
+  std::string k(key);
+  if (k == "tile_bits") {
+    if (value < 11 || value > kMaxTileBits) return fail(PSUM_ERR_INVALID, "tile_bits must be 11..13");
+    h->opt.tile_bits = (int)value;
+  } else if (k == "low_bits") {
+    if (value < 1 || value > 8) return fail(PSUM_ERR_INVALID, "low_bits must be 1..8");
+    h->opt.low_bits = (int)value;
+  } else if (k == "kernel") {
+    if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "kernel must be 0,1,2");
+    h->opt.kernel = (int)value;
+  } else if (k == "min_cover") {
+    if (value < 1) return fail(PSUM_ERR_INVALID, "min_cover must be >= 1");
+    h->opt.min_cover = (int)value;
+  } else {
+    return fail(PSUM_ERR_INVALID, "unknown option %s", key);
+  }
+  h->planned = false;
+  if (h->uploaded) free_device(h);
+  return PSUM_OK;
+}
+
+extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
+  if (!h || !info) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!h->planned) PS_TRY(plan(h));
+  int64_t v[12] = {0};
+  v[0] = h->n;
+  v[1] = (int64_t)h->terms.size();
+  {
+    std::vector<uint64_t> xs;
+    for (auto& t : h->terms) xs.push_back(t.x);
+    std::sort(xs.begin(), xs.end());
+    v[2] = (int64_t)(std::unique(xs.begin(), xs.end()) - xs.begin());
+  }
+  int64_t gparts = 0;
+  for (auto& P : h->parts) {
+    v[3] += (int64_t)P.passes.size();
+    for (auto& ps : P.passes) {
+      v[4] += ps.n_remote;
+      v[8] += (int64_t)ps.pat_zt.size();
+      v[10] = ps.L;
+    }
+    v[9] += (int64_t)P.comp.size();
+    if (P.g != 0) ++gparts;
+  }
+  v[5] = h->hermitian;
+  v[6] = h->diagonal;
+  v[7] = h->n_loc;
+  v[11] = gparts;
+  for (int i = 0; i < n_info && i < 12; ++i) info[i] = v[i];
+  return PSUM_OK;
+}
+
+static PartHost* find_part(psum_handle_s* h, int g) {
+  for (auto& P : h->parts)
+    if (P.g == g) return &P;
+  return nullptr;
+}
+
+extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* n_groups,
+                              int64_t* n_remote_groups, int64_t* n_patterns) {
+  if (!h) return fail(PSUM_ERR_INVALID, "null handle");
+  if (!h->planned) PS_TRY(plan(h));
+  PartHost* P = find_part(h, g);
+  if (!P || p < 0 || p >= (int)P->passes.size()) return fail(PSUM_ERR_INVALID, "no pass %d of part %d", p, g);
+  const PassHost& ps = P->passes[p];
+  if (free_mask) *free_mask = ps.free_mask;
+  if (n_groups) *n_groups = ps.n_xgroups;
+  if (n_remote_groups) *n_remote_groups = ps.n_remote;
+  if (n_patterns) *n_patterns = (int64_t)ps.pat_zt.size();
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch sequencing
+// ---------------------------------------------------------------------------------------------
+// Runs one part.  Expectation partials are appended at d_partial[*pcount...].
+static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, const double2* bra,
+                    double2* y, int accumulate, bool want_expect, size_t* pcount, cudaStream_t st) {
+  const bool bra_is_src = (bra == src) || bra == nullptr;
+  if (!D.passes.empty()) {
+    bool first = true;
+    for (const DevPass& dp : D.passes) {
+      PassParams pp = dp.params;
+      pp.accumulate = (accumulate || !first) ? 1 : 0;
+      double2* part = want_expect ? h->d_partial + *pcount : nullptr;
+      const double2* b = bra_is_src ? nullptr : bra;
+      if (want_expect && *pcount + dp.grid > h->partial_cap)
+        return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
+      if (y && want_expect) k_pass<true, true><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
+      else if (y) k_pass<true, false><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
+      else k_pass<false, true><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
+      if (want_expect) *pcount += dp.grid;
+      first = false;
+    }
+  } else {
+    double2* part = want_expect ? h->d_partial + *pcount : nullptr;
+    if (want_expect && *pcount + D.grid_stream > h->partial_cap)
+      return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
+    k_stream<<<D.grid_stream, kThreads, 0, st>>>(src, bra ? bra : src, y, D.sgroups, D.nsg, D.sterms,
+                                                 n_local_amps(h), accumulate, part);
+    if (want_expect) *pcount += D.grid_stream;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+static int fetch_scalars(psum_handle_s* h, int count, double* out, cudaStream_t st) {
+  CUDA_TRY(cudaMemcpyAsync(h->h_scalar, h->d_scalar, sizeof(double2) * count, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < count; ++i) {
+    out[2 * i] = h->h_scalar[i].x;
+    out[2 * i + 1] = h->h_scalar[i].y;
+  }
+  return PSUM_OK;
+}
+
+static int apply_local(psum_handle_s* h, const double2* psi, const double2* bra, double2* y,
+                       double* expect_out, cudaStream_t st) {
+  if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle is sharded: use psum_apply_sharded / psum_apply_part");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if (!psi || (!y && !expect_out)) return fail(PSUM_ERR_INVALID, "null device pointer");
+  if (y == psi) return fail(PSUM_ERR_INVALID, "y must not alias psi");
+  PS_TRY(upload(h));
+  size_t pcount = 0;
+  for (const DevPart& D : h->dparts)
+    PS_TRY(run_part(h, D, psi, bra, y, 0, expect_out != nullptr, &pcount, st));
+  if (expect_out) {
+    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
+    CUDA_TRY(cudaGetLastError());
+    PS_TRY(fetch_scalars(h, 1, expect_out, st));
+  }
+  return PSUM_OK;
+}
+
+extern "C" int psum_apply(psum_handle_t h, const void* psi_dev, void* y_dev, double* expect_out,
+                          psum_stream_t stream) {
+  if (!h) return fail(PSUM_ERR_INVALID, "null handle");
+  if (!y_dev) return fail(PSUM_ERR_INVALID, "y_dev is NULL");
+  return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, (double2*)y_dev, expect_out,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], psum_stream_t stream) {
+  if (!h || !out) return fail(PSUM_ERR_INVALID, "null argument");
+  return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, nullptr, out, (cudaStream_t)stream);
+}
+
+extern "C" int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, double out[2],
+                              psum_stream_t stream) {
+  if (!h || !out || !phi_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  return apply_local(h, (const double2*)psi_dev, (const double2*)phi_dev, nullptr, out, (cudaStream_t)stream);
+}
+
+extern "C" int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev, double* out,
+                                 psum_stream_t stream) {
+  if (!h || !out || batch < 0) return fail(PSUM_ERR_INVALID, "bad argument");
+  if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle is sharded");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  PS_TRY(upload(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch > 256) return fail(PSUM_ERR_INVALID, "batch > 256");
+  const double2* base = (const double2*)psi_dev;
+  size_t stride_partials = 0;
+  for (int b = 0; b < batch; ++b) {
+    const double2* psi = base + (uint64_t)b * n_local_amps(h);
+    size_t pcount = 0;
+    for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, &pcount, st));
+    stride_partials = pcount;
+    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar + b, 0);
+  }
+  (void)stride_partials;
+  CUDA_TRY(cudaGetLastError());
+  if (batch) PS_TRY(fetch_scalars(h, batch, out, st));
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagonal operators
+// ---------------------------------------------------------------------------------------------
+extern "C" int psum_diag(psum_handle_t h, double* d_dev, psum_stream_t stream) {
+  if (!h || !d_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!h->diagonal) return fail(PSUM_ERR_NOT_DIAGONAL, "operator has X/Y terms");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  PS_TRY(upload(h));
+  const DevPart* D0 = nullptr;
+  for (auto& D : h->dparts)
+    if (D.g == 0) D0 = &D;
+  if (!D0) return fail(PSUM_ERR_INVALID, "no local part");
+  // the streaming plan of a diagonal operator is one group holding every term (z local part);
+  // the rank sign of the global z-part is already folded into the coefficients.
+  k_diag<<<D0->grid_stream, kThreads, 0, (cudaStream_t)stream>>>(d_dev, D0->sterms, D0->nst,
+                                                                n_local_amps(h), 0);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+extern "C" int psum_diag_kmin(psum_handle_t h, int k, double* vals, uint64_t* idx, psum_stream_t stream) {
+  if (!h || !vals || !idx || k < 1) return fail(PSUM_ERR_INVALID, "bad argument");
+  if (h->world != 1) return fail(PSUM_ERR_INVALID, "diag_kmin on a sharded handle: reduce per-rank results on the host");
+  const uint64_t N = n_local_amps(h);
+  if ((uint64_t)k > N) return fail(PSUM_ERR_INVALID, "k > 2^n");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, N * sizeof(double)));
+  int rc = psum_diag(h, d, stream);
+  if (rc != PSUM_OK) {
+    cudaFree(d);
+    return rc;
+  }
+  const int grid = (int)std::min<uint64_t>((N + kThreads - 1) / kThreads, (uint64_t)h->num_sms * 8);
+  ValIdx* part = nullptr;
+  ValIdx* hpart = (ValIdx*)malloc(sizeof(ValIdx) * grid);
+  cudaError_t e = cudaMalloc(&part, sizeof(ValIdx) * grid);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    free(hpart);
+    return fail(PSUM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  ValIdx lo{0.0, 0};
+  for (int j = 0; j < k; ++j) {
+    k_argmin_after<<<grid, kThreads, 0, st>>>(d, N, lo, j > 0, part);
+    cudaMemcpyAsync(hpart, part, sizeof(ValIdx) * grid, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) break;
+    ValIdx best = hpart[0];
+    for (int b = 1; b < grid; ++b)
+      if (hpart[b].v < best.v || (hpart[b].v == best.v && hpart[b].i < best.i)) best = hpart[b];
+    vals[j] = best.v;
+    idx[j] = best.i;
+    lo = best;
+  }
+  cudaFree(part);
+  cudaFree(d);
+  free(hpart);
+  if (e != cudaSuccess) return fail(PSUM_ERR_CUDA, "diag_kmin: %s", cudaGetErrorString(e));
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector helpers
+// ---------------------------------------------------------------------------------------------
+static int vec_grid(uint64_t n) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + kThreads - 1) / kThreads, (uint64_t)sms * 8));
+}
+
+extern "C" int psum_fill_state(void* psi_dev, uint64_t n_amps, uint64_t first_index, uint64_t seed,
+                               psum_stream_t stream) {
+  if (!psi_dev) return fail(PSUM_ERR_INVALID, "null pointer");
+  k_fill_state<<<vec_grid(n_amps), kThreads, 0, (cudaStream_t)stream>>>((double2*)psi_dev, n_amps, first_index, seed);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+// scratch for the handle-less vector helpers
+struct VecScratch {
+  double2* d = nullptr;
+  double2* h = nullptr;
+  int cap = 0;
+};
+static thread_local VecScratch g_vs;
+static int vec_scratch(int need) {
+  if (g_vs.cap >= need) return PSUM_OK;
+  if (g_vs.d) cudaFree(g_vs.d);
+  if (g_vs.h) cudaFreeHost(g_vs.h);
+  g_vs.cap = 0;
+  CUDA_TRY(cudaMalloc(&g_vs.d, sizeof(double2) * (need + 1)));
+  CUDA_TRY(cudaMallocHost(&g_vs.h, sizeof(double2) * 4));
+  g_vs.cap = need;
+  return PSUM_OK;
+}
+
+extern "C" int psum_vec_dot(const void* a_dev, const void* b_dev, uint64_t n_amps, double out[2],
+                            psum_stream_t stream) {
+  if (!a_dev || !b_dev || !out) return fail(PSUM_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = vec_grid(n_amps);
+  PS_TRY(vec_scratch(grid));
+  k_dot<<<grid, kThreads, 0, st>>>((const double2*)a_dev, (const double2*)b_dev, n_amps, g_vs.d);
+  k_reduce_partials<<<1, kThreads, 0, st>>>(g_vs.d, grid, g_vs.d + grid, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(g_vs.h, g_vs.d + grid, sizeof(double2), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  out[0] = g_vs.h[0].x;
+  out[1] = g_vs.h[0].y;
+  return PSUM_OK;
+}
+
+extern "C" int psum_vec_scale(void* a_dev, uint64_t n_amps, double s_re, double s_im, psum_stream_t stream) {
+  if (!a_dev) return fail(PSUM_ERR_INVALID, "null pointer");
+  k_scale<<<vec_grid(n_amps), kThreads, 0, (cudaStream_t)stream>>>((double2*)a_dev, n_amps, s_re, s_im);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+extern "C" int psum_vec_axpy(void* y_dev, const void* x_dev, uint64_t n_amps, double a_re, double a_im,
+                             psum_stream_t stream) {
+  if (!y_dev || !x_dev) return fail(PSUM_ERR_INVALID, "null pointer");
+  k_axpy<<<vec_grid(n_amps), kThreads, 0, (cudaStream_t)stream>>>((double2*)y_dev, (const double2*)x_dev, n_amps, a_re, a_im);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharding
+// ---------------------------------------------------------------------------------------------
+extern "C" int psum_nccl_unique_id(void* out128) {
+  if (!out128) return fail(PSUM_ERR_INVALID, "null pointer");
+  PS_TRY(load_nccl());
+  nccl_uid_t id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return PSUM_OK;
+}
+
+extern "C" int psum_shard_init(psum_handle_t h, int rank, int world, const void* unique_id128) {
+  if (!h) return fail(PSUM_ERR_INVALID, "null handle");
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+    return fail(PSUM_ERR_INVALID, "world must be a power of two and 0 <= rank < world");
+  int p = 0;
+  while ((1 << p) < world) ++p;
+  if (p >= h->n) return fail(PSUM_ERR_INVALID, "world too large for %d qubits", h->n);
+  h->p_bits = p;
+  h->rank = rank;
+  h->world = world;
+  h->n_loc = h->n - p;
+  PS_TRY(plan(h));
+  if (unique_id128 && world > 1) {
+    PS_TRY(load_nccl());
+    nccl_uid_t id;
+    memcpy(&id, unique_id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_recv[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
+    }
+  }
+  return PSUM_OK;
+}
+
+extern "C" int psum_shard_terms(psum_handle_t h, int g, int64_t cap, uint64_t* x_local, uint64_t* z_local,
+                                double* coeff_re_im, int64_t* n_out) {
+  if (!h || !n_out) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!h->planned) PS_TRY(plan(h));
+  PartHost* P = find_part(h, g);
+  int64_t n = P ? (int64_t)P->comp.size() : 0;
+  *n_out = n;
+  if (!P || cap < n || !x_local || !z_local || !coeff_re_im) return PSUM_OK;
+  for (int64_t i = 0; i < n; ++i) {
+    x_local[i] = P->comp[i].xl;
+    z_local[i] = P->comp[i].zl;
+    coeff_re_im[2 * i] = P->comp[i].im ? 0.0 : P->comp[i].val;
+    coeff_re_im[2 * i + 1] = P->comp[i].im ? P->comp[i].val : 0.0;
+  }
+  return PSUM_OK;
+}
+
+extern "C" int psum_apply_part(psum_handle_t h, int g, const void* src_dev, const void* bra_dev, void* y_dev,
+                               int accumulate, double* expect_acc, psum_stream_t stream) {
+  if (!h || !src_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!y_dev && !expect_acc) return fail(PSUM_ERR_INVALID, "nothing to compute");
+  PS_TRY(upload(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevPart* D = nullptr;
+  for (auto& d : h->dparts)
+    if (d.g == g) D = &d;
+  if (!D) {  // no term has this global part: contribution is zero
+    if (y_dev && !accumulate) CUDA_TRY(cudaMemsetAsync(y_dev, 0, n_local_amps(h) * sizeof(double2), st));
+    return PSUM_OK;
+  }
+  size_t pcount = 0;
+  const double2* bra = bra_dev ? (const double2*)bra_dev : (const double2*)src_dev;
+  PS_TRY(run_part(h, *D, (const double2*)src_dev, bra, (double2*)y_dev, accumulate, expect_acc != nullptr, &pcount, st));
+  if (expect_acc) {
+    double v[2];
+    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
+    CUDA_TRY(cudaGetLastError());
+    PS_TRY(fetch_scalars(h, 1, v, st));
+    expect_acc[0] += v[0];
+    expect_acc[1] += v[1];
+  }
+  return PSUM_OK;
+}
+
+extern "C" int psum_allreduce_sum(psum_handle_t h, double* host_vals, int n) {
+  if (!h || !host_vals || n < 0 || n > 256) return fail(PSUM_ERR_INVALID, "bad argument");
+  if (h->world == 1) return PSUM_OK;
+  if (!h->comm) return fail(PSUM_ERR_NCCL, "no communicator (psum_shard_init without id)");
+  PS_TRY(upload(h));
+  double* d = (double*)h->d_scalar;
+  double* hs = (double*)h->h_scalar;
+  for (int i = 0; i < n; ++i) hs[i] = host_vals[i];
+  CUDA_TRY(cudaMemcpyAsync(d, hs, sizeof(double) * n, cudaMemcpyHostToDevice, h->comm_stream));
+  NCCL_TRY(g_nccl.AllReduce(d, d, n, kNcclFloat64, kNcclSum, h->comm, h->comm_stream));
+  CUDA_TRY(cudaMemcpyAsync(hs, d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->comm_stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  for (int i = 0; i < n; ++i) host_vals[i] = hs[i];
+  return PSUM_OK;
+}
+
+// Sharded H.psi: the local part runs on `stream` while the first partner shard is exchanged on the
+// communication stream; each further global part g alternates between the two halves of recv_dev
+// when it holds >= 2 shards, so exchange g+1 overlaps the passes over the shard of g.
+extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
+                                  uint64_t recv_amps, double* expect_out, psum_stream_t stream) {
+  if (!h || !psi_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!y_dev && !expect_out) return fail(PSUM_ERR_INVALID, "nothing to compute");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  PS_TRY(upload(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t N = n_local_amps(h);
+  const double2* psi = (const double2*)psi_dev;
+  double2* y = (double2*)y_dev;
+  bool any_remote = false;
+  for (auto& D : h->dparts)
+    if (D.g != 0) any_remote = true;
+  if (any_remote) {
+    if (!h->comm) return fail(PSUM_ERR_NCCL, "terms with global x-parts need a communicator");
+    if (!recv_dev || recv_amps < N) return fail(PSUM_ERR_INVALID, "recv_dev must hold one shard");
+  }
+  const int nbuf = (recv_amps >= 2 * N) ? 2 : 1;
+  size_t pcount = 0;
+  bool wrote_y = false;
+  if (any_remote) {
+    CUDA_TRY(cudaEventRecord(h->ev_ready, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  }
+  // local part first (overlaps the first exchange)
+  int slot = 0;
+  std::vector<const DevPart*> remote;
+  for (auto& D : h->dparts)
+    if (D.g != 0) remote.push_back(&D);
+  auto post_exchange = [&](const DevPart* D, int s, bool must_wait_used) -> int {
+    if (must_wait_used) CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_used[s], 0));
+    double2* buf = (double2*)recv_dev + (uint64_t)s * N;
+    const int peer = h->rank ^ D->g;
+    NCCL_TRY(g_nccl.GroupStart());
+    NCCL_TRY(g_nccl.Send(psi, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
+    NCCL_TRY(g_nccl.Recv(buf, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    CUDA_TRY(cudaEventRecord(h->ev_recv[s], h->comm_stream));
+    return PSUM_OK;
+  };
+  std::vector<bool> used_once(2, false);
+  if (!remote.empty()) PS_TRY(post_exchange(remote[0], 0, false));
+  for (auto& D : h->dparts)
+    if (D.g == 0) {
+      PS_TRY(run_part(h, D, psi, psi, y, 0, expect_out != nullptr, &pcount, st));
+      wrote_y = true;
+    }
+  if (!wrote_y && y) CUDA_TRY(cudaMemsetAsync(y, 0, N * sizeof(double2), st));
+  for (size_t r = 0; r < remote.size(); ++r) {
+    slot = (int)(r % nbuf);
+    // prefetch the next exchange into the other buffer
+    if (nbuf == 2 && r + 1 < remote.size()) {
+      int ns = (int)((r + 1) % 2);
+      PS_TRY(post_exchange(remote[r + 1], ns, used_once[ns]));
+    }
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_recv[slot], 0));
+    const double2* buf = (const double2*)recv_dev + (uint64_t)slot * N;
+    PS_TRY(run_part(h, *remote[r], buf, psi, y, 1, expect_out != nullptr, &pcount, st));
+    CUDA_TRY(cudaEventRecord(h->ev_used[slot], st));
+    used_once[slot] = true;
+    if (nbuf == 1 && r + 1 < remote.size()) PS_TRY(post_exchange(remote[r + 1], 0, true));
+  }
+  if (expect_out) {
+    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
+    CUDA_TRY(cudaGetLastError());
+    if (h->comm) NCCL_TRY(g_nccl.AllReduce(h->d_scalar, h->d_scalar, 2, kNcclFloat64, kNcclSum, h->comm, st));
+    PS_TRY(fetch_scalars(h, 1, expect_out, st));
+  }
+  return PSUM_OK;
+}
+
+#include "psum_lanczos.inc"

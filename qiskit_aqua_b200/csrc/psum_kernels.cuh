@@ -1,0 +1,491 @@
+// psum_kernels.cuh -- sm_100a device code of the Pauli-sum engine.
+//
+//   y[i] = sum_g D_g(i) * src[i ^ x_g],   D_g(i) = sum_{k in g} c'_k (-1)^{popc(i & z_k)}
+//
+// Kernel B (k_pass) is the product path.  One launch = one "pass": a free set S of L qubits
+// defines tiles (the 2^L amplitudes that differ only in S).  A CTA stages one tile of the source
+// vector in shared memory with cp.async, and every x-group whose mask lies inside S reads its
+// partner amplitudes from that tile -- psi is read from HBM once per pass, not once per group.
+// Signs are never evaluated per (term, amplitude):
+//   * bits outside S:   folded into the coefficient once per (tile, term)      ("fold")
+//   * equal in-tile z-patterns of one group are merged into one pattern          ("compaction")
+//   * tile bits 5..7 (the 8 amplitudes a thread owns): patterns are summed per class
+//     zr = (zt >> 5) & 7 and an 8-point Walsh-Hadamard butterfly expands them    ("class sums")
+//   * the remaining tile bits: one popc per (pattern, thread)
+// Kernel A (k_stream) is the plain streaming form used for n_loc < 11 qubits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "psum_plan.h"
+
+namespace psum {
+
+constexpr int kThreads = 256;
+constexpr int kAmpsPerThread = 8;
+constexpr int kRoundAmps = kThreads * kAmpsPerThread;  // 2048
+
+struct PassParams {
+  const GroupRec* groups;
+  const uint16_t* pat_zt;
+  const uint32_t* pat_tptr;
+  const uint64_t* term_zb;
+  const double* term_val;
+  const ChunkRec* chunks;
+  int nchunks;
+  int L;
+  int n_nonfree;
+  int accumulate;
+  uint64_t ntiles;
+  uint8_t fbit[16];  // positions of the free bits, ascending
+  uint8_t nbit[64];  // positions of the non-free local bits, ascending
+};
+
+__device__ __forceinline__ double flip_sign(double v, int s) {
+  return __hiloint2double(__double2hiint(v) ^ (s << 31), __double2loint(v));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void wht8(double* v) {
+#pragma unroll
+  for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+    for (int i = 0; i < 8; i += 2 * h)
+#pragma unroll
+      for (int j = i; j < i + h; ++j) {
+        double a = v[j], b = v[j + h];
+        v[j] = a + b;
+        v[j + h] = a - b;
+      }
+}
+
+// deterministic block reduction of a complex value; result valid in thread 0
+__device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = l < nw ? scratch[l] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+      v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+    }
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel B: one pass over all tiles of a free set.
+//   STORE : write / accumulate y
+//   EXPECT: accumulate sum conj(bra_i) * contribution_i into partial[blockIdx.x]
+//   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
+// ------------------------------------------------------------------------------------------
+template <bool STORE, bool EXPECT>
+__global__ void __launch_bounds__(kThreads, 2)
+k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
+       const PassParams P, double2* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = P.L;
+  const uint32_t tile_amps = 1u << L;
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  double* cf = reinterpret_cast<double*>(tile + tile_amps);
+  uint64_t* offHi = reinterpret_cast<uint64_t*>(cf + kPatChunk);
+  GroupRec* grp = reinterpret_cast<GroupRec*>(offHi + 32);
+  uint16_t* zts = reinterpret_cast<uint16_t*>(grp + kGrpChunk);
+  double2* red = reinterpret_cast<double2*>(zts + kPatChunk);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // deposit tables: offset of tile element e = offLo8[e & 255] | offHi[e >> 8]
+  uint64_t offLo8 = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) offLo8 |= (uint64_t)((tid >> j) & 1) << P.fbit[j];
+  const uint64_t offLane = offLo8 & ((1ull << P.fbit[0]) | (1ull << P.fbit[1]) | (1ull << P.fbit[2]) |
+                                     (1ull << P.fbit[3]) | (1ull << P.fbit[4]));
+  if (tid < 32) {
+    uint64_t o = 0;
+    for (int j = 8; j < L; ++j) o |= (uint64_t)((tid >> (j - 8)) & 1) << P.fbit[j];
+    offHi[tid] = o;
+  }
+  const uint64_t b5 = 1ull << P.fbit[5], b6 = 1ull << P.fbit[6], b7 = 1ull << P.fbit[7];
+  const int nrounds = (int)(tile_amps / kRoundAmps);
+  const int nload = (int)(tile_amps / kThreads);
+
+  double2 eacc = make_double2(0.0, 0.0);
+
+  for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
+    uint64_t base = 0;
+    for (int j = 0; j < P.n_nonfree; ++j) base |= ((tile_id >> j) & 1ull) << P.nbit[j];
+
+    __syncthreads();  // previous tile fully consumed; offHi visible on the first trip
+    for (int j = 0; j < nload; ++j)
+      cp_async16(&tile[j * kThreads + tid], &src[base | offLo8 | offHi[j]]);
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int rnd = 0; rnd < nrounds; ++rnd) {
+      const uint32_t t0 = (uint32_t)rnd * kRoundAmps + (uint32_t)warp * 256u + (uint32_t)lane;
+      const uint64_t i0 = base | offLane | offHi[rnd * 8 + warp];
+      double2 yacc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) yacc[r] = make_double2(0.0, 0.0);
+
+      for (int c = 0; c < P.nchunks; ++c) {
+        const ChunkRec ch = P.chunks[c];
+        __syncthreads();  // everyone is done with the previous chunk's cf / grp / zts
+        for (int p = tid; p < ch.np; p += kThreads) {
+          const int gp = ch.p0 + p;
+          const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
+          double v = 0.0;
+          for (uint32_t t = ta; t < tb; ++t)
+            v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+          cf[p] = v;
+          zts[p] = P.pat_zt[gp];
+        }
+        for (int g = tid; g < ch.ng * 2; g += kThreads)
+          reinterpret_cast<uint4*>(grp)[g] =
+              reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
+        __syncthreads();
+
+        for (int g = 0; g < ch.ng; ++g) {
+          const uint4 hdr = reinterpret_cast<const uint4*>(grp)[2 * g];
+          const uint4 cw = reinterpret_cast<const uint4*>(grp)[2 * g + 1];
+          const uint32_t xt = hdr.x & 0x7fffffffu;
+          const bool remote = (hdr.x >> 31) != 0;
+          int p = (int)hdr.y;
+          const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w};
+          double S[16];
+#pragma unroll
+          for (int cls = 0; cls < 16; ++cls) {
+            S[cls] = 0.0;
+            const int cnt = (int)((cwv[cls >> 2] >> (8 * (cls & 3))) & 255u);
+            for (int j = 0; j < cnt; ++j, ++p)
+              S[cls] += flip_sign(cf[p], __popc((uint32_t)zts[p] & t0) & 1);
+          }
+          const bool has_im = (cw.z | cw.w) != 0u;
+          const bool re_flat = (cw.x <= 255u) && cw.y == 0u;  // only class 0 populated
+          const bool im_flat = (cw.z <= 255u) && cw.w == 0u;
+          if (!re_flat) wht8(S);
+          else {
+#pragma unroll
+            for (int r = 1; r < 8; ++r) S[r] = S[0];
+          }
+          if (has_im) {
+            if (!im_flat) wht8(S + 8);
+            else {
+#pragma unroll
+              for (int r = 1; r < 8; ++r) S[8 + r] = S[8];
+            }
+          }
+          double2 pv[8];
+          if (!remote) {
+            const uint32_t tp = t0 ^ xt;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
+          } else {
+            const uint64_t ip = i0 ^ ((uint64_t)hdr.z | ((uint64_t)hdr.w << 32));
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              pv[r] = __ldg(&src[ip ^ ((r & 1) ? b5 : 0ull) ^ ((r & 2) ? b6 : 0ull) ^
+                                 ((r & 4) ? b7 : 0ull)]);
+          }
+          if (has_im) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              yacc[r].x += S[r] * pv[r].x - S[8 + r] * pv[r].y;
+              yacc[r].y += S[r] * pv[r].y + S[8 + r] * pv[r].x;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              yacc[r].x += S[r] * pv[r].x;
+              yacc[r].y += S[r] * pv[r].y;
+            }
+          }
+        }
+      }
+      // epilogue of the round: y and/or the expectation partial
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint64_t ir = i0 | ((r & 1) ? b5 : 0ull) | ((r & 2) ? b6 : 0ull) | ((r & 4) ? b7 : 0ull);
+        if (EXPECT) {
+          const double2 b = bra ? __ldg(&bra[ir]) : tile[t0 | ((uint32_t)r << 5)];
+          eacc.x += b.x * yacc[r].x + b.y * yacc[r].y;
+          eacc.y += b.x * yacc[r].y - b.y * yacc[r].x;
+        }
+        if (STORE) {
+          double2 o = yacc[r];
+          if (P.accumulate) {
+            const double2 old = y[ir];
+            o.x += old.x;
+            o.y += old.y;
+          }
+          y[ir] = o;
+        }
+      }
+    }
+  }
+  if (EXPECT) {
+    double2 tot = block_reduce(eacc, red);
+    if (tid == 0) partial[blockIdx.x] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel A: streaming form, one amplitude per thread (grid-stride).  Any n_loc >= 0.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_stream(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
+         const SimpleGroup* __restrict__ groups, int ngroups, const SimpleTerm* __restrict__ terms,
+         uint64_t n_amps, int accumulate, double2* __restrict__ partial) {
+  __shared__ double2 red[kThreads / 32];
+  double2 eacc = make_double2(0.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int g = 0; g < ngroups; ++g) {
+      const SimpleGroup G = groups[g];
+      double dre = 0.0, dim = 0.0;
+      for (int t = G.t0; t < G.t0 + G.nt; ++t) {
+        const SimpleTerm T = terms[t];
+        const int s = __popcll(i & T.z) & 1;
+        dre += flip_sign(T.re, s);
+        dim += flip_sign(T.im, s);
+      }
+      const double2 p = src[i ^ G.xl];
+      acc.x += dre * p.x - dim * p.y;
+      acc.y += dre * p.y + dim * p.x;
+    }
+    if (partial) {
+      const double2 b = bra[i];
+      eacc.x += b.x * acc.x + b.y * acc.y;
+      eacc.y += b.x * acc.y - b.y * acc.x;
+    }
+    if (y) {
+      if (accumulate) {
+        const double2 old = y[i];
+        acc.x += old.x;
+        acc.y += old.y;
+      }
+      y[i] = acc;
+    }
+  }
+  if (partial) {
+    double2 tot = block_reduce(eacc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  }
+}
+
+// sum `count` complex partials in a fixed order -> out[0]  (single block)
+__global__ void __launch_bounds__(kThreads)
+k_reduce_partials(const double2* __restrict__ partial, int count, double2* __restrict__ out,
+                  int accumulate) {
+  __shared__ double2 red[kThreads / 32];
+  double2 v = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    v.x += partial[i].x;
+    v.y += partial[i].y;
+  }
+  double2 tot = block_reduce(v, red);
+  if (threadIdx.x == 0) {
+    if (accumulate) {
+      tot.x += out[0].x;
+      tot.y += out[0].y;
+    }
+    out[0] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// vector helpers (Lanczos, synthetic states)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// uniform in [-0.5, 0.5), exactly representable -> bit-identical on host and device
+__host__ __device__ __forceinline__ double counter_uniform(uint64_t seed, uint64_t ctr) {
+  const uint64_t h = splitmix64(seed ^ splitmix64(ctr));
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+__global__ void k_fill_state(double2* psi, uint64_t n_amps, uint64_t first, uint64_t seed) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t gi = first + i;
+    psi[i] = make_double2(counter_uniform(seed, 2 * gi), counter_uniform(seed, 2 * gi + 1));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dot(const double2* __restrict__ a, const double2* __restrict__ b, uint64_t n_amps,
+      double2* __restrict__ partial) {
+  __shared__ double2 red[kThreads / 32];
+  double2 v = make_double2(0.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 p = a[i], q = b[i];
+    v.x += p.x * q.x + p.y * q.y;
+    v.y += p.x * q.y - p.y * q.x;
+  }
+  double2 tot = block_reduce(v, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// y = y * s  (complex scalar from device memory: sdev[0] if sdev else (sre, sim))
+__global__ void k_scale(double2* a, uint64_t n_amps, double sre, double sim) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 p = a[i];
+    a[i] = make_double2(p.x * sre - p.y * sim, p.x * sim + p.y * sre);
+  }
+}
+
+__global__ void k_axpy(double2* __restrict__ y, const double2* __restrict__ x, uint64_t n_amps,
+                       double are, double aim) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 p = x[i];
+    double2 q = y[i];
+    q.x += are * p.x - aim * p.y;
+    q.y += are * p.y + aim * p.x;
+    y[i] = q;
+  }
+}
+
+// Lanczos fused update: w = w - alpha*v - beta*vprev ; partial = |w|^2
+__global__ void __launch_bounds__(kThreads)
+k_lanczos_update(double2* __restrict__ w, const double2* __restrict__ v,
+                 const double2* __restrict__ vprev, uint64_t n_amps, double alpha, double beta,
+                 double2* __restrict__ partial) {
+  __shared__ double2 red[kThreads / 32];
+  double2 acc = make_double2(0.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 q = w[i];
+    const double2 p = v[i];
+    q.x -= alpha * p.x;
+    q.y -= alpha * p.y;
+    if (vprev) {
+      const double2 o = vprev[i];
+      q.x -= beta * o.x;
+      q.y -= beta * o.y;
+    }
+    w[i] = q;
+    acc.x += q.x * q.x + q.y * q.y;
+  }
+  double2 tot = block_reduce(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// out[j] = <basis_j | w> for j in [0,m): one block row per j (gridDim.y = m)
+__global__ void __launch_bounds__(kThreads)
+k_multi_dot(const double2* __restrict__ basis, uint64_t stride, const double2* __restrict__ w,
+            uint64_t n_amps, double2* __restrict__ partial) {
+  __shared__ double2 red[kThreads / 32];
+  const double2* a = basis + (uint64_t)blockIdx.y * stride;
+  double2 v = make_double2(0.0, 0.0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 p = a[i], q = w[i];
+    v.x += p.x * q.x + p.y * q.y;
+    v.y += p.x * q.y - p.y * q.x;
+  }
+  double2 tot = block_reduce(v, red);
+  if (threadIdx.x == 0) partial[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// w -= sum_j coef[j] * basis_j   (coef on device, m vectors)
+__global__ void k_multi_axpy(double2* __restrict__ w, const double2* __restrict__ basis,
+                             uint64_t stride, int m, const double2* __restrict__ coef,
+                             uint64_t n_amps, double sign) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 q = w[i];
+    for (int j = 0; j < m; ++j) {
+      const double2 c = coef[j];
+      const double2 p = basis[(uint64_t)j * stride + i];
+      q.x += sign * (c.x * p.x - c.y * p.y);
+      q.y += sign * (c.x * p.y + c.y * p.x);
+    }
+    w[i] = q;
+  }
+}
+
+// reduce m rows of `cols` partials each -> out[j]
+__global__ void __launch_bounds__(kThreads)
+k_reduce_rows(const double2* __restrict__ partial, int cols, double2* __restrict__ out) {
+  __shared__ double2 red[kThreads / 32];
+  const double2* row = partial + (uint64_t)blockIdx.x * cols;
+  double2 v = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    v.x += row[i].x;
+    v.y += row[i].y;
+  }
+  double2 tot = block_reduce(v, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
+// diagonal of an all-Z sum: d[i] = sum_k re_k (-1)^{popc(i & z_k)}
+__global__ void k_diag(double* __restrict__ d, const SimpleTerm* __restrict__ terms, int nterms,
+                       uint64_t n_amps, uint64_t first_index_sign_mask_unused) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int t = 0; t < nterms; ++t) v += flip_sign(terms[t].re, __popcll(i & terms[t].z) & 1);
+    d[i] = v;
+  }
+}
+
+// lexicographic (value, index) minimum strictly greater than (lo_val, lo_idx)
+struct ValIdx {
+  double v;
+  uint64_t i;
+};
+__device__ __forceinline__ bool vi_less(const ValIdx& a, const ValIdx& b) {
+  return a.v < b.v || (a.v == b.v && a.i < b.i);
+}
+__global__ void __launch_bounds__(kThreads)
+k_argmin_after(const double* __restrict__ d, uint64_t n_amps, ValIdx lo, int have_lo,
+               ValIdx* __restrict__ partial) {
+  __shared__ ValIdx red[kThreads / 32];
+  ValIdx best{1.0 / 0.0, ~0ull};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    ValIdx c{d[i], i};
+    if (have_lo && !vi_less(lo, c)) continue;
+    if (vi_less(c, best)) best = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ValIdx other{__shfl_down_sync(0xffffffffu, best.v, o), __shfl_down_sync(0xffffffffu, best.i, o)};
+    if (vi_less(other, best)) best = other;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 1; j < kThreads / 32; ++j)
+      if (vi_less(red[j], best)) best = red[j];
+    partial[blockIdx.x] = best;
+  }
+}
+
+}  // namespace psum

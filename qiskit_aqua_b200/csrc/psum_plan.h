@@ -1,0 +1,354 @@
+// psum_plan.h -- host-side packing and pass planning for the Pauli-sum engine (no CUDA here).
+//
+// Replaces the reference's container logic only in the sense of "pack once":
+//   WeightedPauliOperator.simplify (legacy/weighted_pauli_operator.py:341-400)  -> merge_terms
+// Everything else (grouping by x-mask, free-bit tiling, pattern compaction) has no reference
+// counterpart: the reference materialises a CSR matrix instead (legacy/op_converter.py:120-123).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+#include <vector>
+
+namespace psum {
+
+static inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+static inline uint64_t low_mask(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
+
+// compress the bits of v selected by mask (ascending) into the low bits
+static inline uint64_t pext64(uint64_t v, uint64_t mask) {
+  uint64_t out = 0;
+  int j = 0;
+  for (uint64_t m = mask; m; m &= m - 1, ++j) {
+    int b = __builtin_ctzll(m);
+    out |= ((v >> b) & 1ull) << j;
+  }
+  return out;
+}
+
+struct MergedTerm {  // one label Pauli after merging duplicates; c = coeff * (-i)^ypow
+  uint64_t x, z;
+  double re, im;
+};
+
+struct CompTerm {  // real-valued component term of one shard/part: value * (im ? i : 1)
+  uint64_t xl, zl;  // local x / z masks
+  double val;
+  uint8_t im;
+};
+
+// ---- device-facing records (layout shared with the kernels) --------------------------------
+struct GroupRec {    // 32 bytes
+  uint32_t xt;       // tile-local xor (compressed free-set bits of x); bit31 = remote flag
+  uint32_t pat0;     // first pattern, relative to the chunk's first pattern
+  uint64_t xl;       // full local x mask (partner index = i ^ xl)
+  uint8_t cnt[16];   // patterns per class: cls = im*8 + ((zt >> 5) & 7)
+};
+static_assert(sizeof(GroupRec) == 32, "GroupRec layout");
+
+struct ChunkRec {  // 16 bytes
+  int32_t g0, ng, p0, np;
+};
+
+constexpr int kMaxTileBits = 13;
+constexpr int kRegBitLo = 5;     // tile bits 5..7 live in registers (8 amplitudes per thread)
+constexpr int kPatChunk = 1024;  // patterns staged in shared memory at a time
+constexpr int kGrpChunk = 128;   // groups staged in shared memory at a time
+
+struct PassHost {
+  int L = 0;                   // tile bits
+  uint64_t free_mask = 0;      // over local qubits
+  std::vector<GroupRec> groups;
+  std::vector<uint16_t> pat_zt;
+  std::vector<uint32_t> pat_tptr;  // size patterns+1
+  std::vector<uint64_t> term_zb;
+  std::vector<double> term_val;
+  std::vector<ChunkRec> chunks;
+  int64_t n_xgroups = 0, n_remote = 0;
+};
+
+struct SimpleTerm {  // for the streaming kernel A: complex coefficient per (x,z)
+  uint64_t z;
+  double re, im;
+};
+struct SimpleGroup {
+  uint64_t xl;
+  int32_t t0, nt;
+};
+
+struct PartHost {  // all terms whose global x-part is g
+  int g = 0;
+  std::vector<CompTerm> comp;          // component terms (rank sign folded in)
+  std::vector<PassHost> passes;        // tiled plan (kernel B)
+  std::vector<SimpleGroup> sgroups;    // streaming plan (kernel A)
+  std::vector<SimpleTerm> sterms;
+  int64_t n_xgroups = 0;
+};
+
+struct PlanOptions {
+  int tile_bits = 12;
+  int low_bits = 4;
+  int min_cover = 3;
+  int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
+};
+
+// -------------------------------------------------------------------------------------------
+inline std::vector<MergedTerm> merge_terms(int64_t T, const uint64_t* x, const uint64_t* z,
+                                           const uint8_t* ypow, const double* c) {
+  std::vector<MergedTerm> out;
+  std::unordered_map<uint64_t, std::vector<int>> index;  // hash(x,z) -> candidates
+  out.reserve(T);
+  for (int64_t k = 0; k < T; ++k) {
+    double re = c[2 * k], im = c[2 * k + 1];
+    // multiply by (-i)^ypow
+    switch (ypow ? (ypow[k] & 3) : 0) {
+      case 1: { double t = re; re = im; im = -t; } break;       // (a+bi)(-i) = b - ai
+      case 2: re = -re; im = -im; break;
+      case 3: { double t = re; re = -im; im = t; } break;       // (a+bi)(i) = -b + ai
+      default: break;
+    }
+    uint64_t key = x[k] * 0x9E3779B97F4A7C15ull ^ (z[k] + 0x7F4A7C15ull + (x[k] << 6));
+    auto& cand = index[key];
+    bool found = false;
+    for (int id : cand)
+      if (out[id].x == x[k] && out[id].z == z[k]) {
+        out[id].re += re;
+        out[id].im += im;
+        found = true;
+        break;
+      }
+    if (!found) {
+      cand.push_back((int)out.size());
+      out.push_back({x[k], z[k], re, im});
+    }
+  }
+  std::vector<MergedTerm> kept;
+  kept.reserve(out.size());
+  for (auto& t : out)
+    if (t.re != 0.0 || t.im != 0.0) kept.push_back(t);  // chop(0.0): drop exact zeros
+  return kept;
+}
+
+// Greedy choice of free-bit sets.  masks = distinct local x-masks of one part.
+// Returns for each pass its free mask and the indices (into masks) it serves; groups that fit no
+// pass ("remote": partner tile read from global memory) are appended to pass 0.
+struct PassChoice {
+  uint64_t free_mask;
+  std::vector<int> members;
+};
+
+inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks, int n_loc, int L,
+                                             int c, int min_cover) {
+  std::vector<PassChoice> passes;
+  L = std::min(L, n_loc);
+  c = std::min(c, L);
+  const uint64_t low = low_mask(c);
+  const uint64_t all = low_mask(n_loc);
+  std::vector<int> uncovered, remote;
+  for (int i = 0; i < (int)masks.size(); ++i) {
+    if (popc64(masks[i] & ~low) <= L - c) uncovered.push_back(i);
+    else remote.push_back(i);
+  }
+  auto fill_mask = [&](uint64_t S) {  // pad with the lowest unused bits up to L bits
+    for (int b = 0; b < n_loc && popc64(S) < L; ++b) S |= (1ull << b);
+    return S;
+  };
+  while (!uncovered.empty()) {
+    uint64_t S = low;
+    int remaining = L - c;
+    while (remaining > 0) {
+      double score[64];
+      for (int b = 0; b < 64; ++b) score[b] = 0.0;
+      bool any = false;
+      for (int i : uncovered) {
+        uint64_t need = masks[i] & ~S;
+        int nn = popc64(need);
+        if (nn == 0 || nn > remaining) continue;
+        any = true;
+        double w = 1.0 / (double)(nn * nn);
+        for (uint64_t m = need; m; m &= m - 1) score[__builtin_ctzll(m)] += w;
+      }
+      if (!any) break;
+      int best = -1;
+      for (int b = 0; b < n_loc; ++b)
+        if (!(S >> b & 1ull) && (best < 0 || score[b] > score[best])) best = b;
+      if (best < 0 || score[best] <= 0.0) break;
+      S |= 1ull << best;
+      --remaining;
+    }
+    S = fill_mask(S) & all;
+    PassChoice pc;
+    pc.free_mask = S;
+    std::vector<int> rest;
+    for (int i : uncovered) {
+      if ((masks[i] & ~S) == 0) pc.members.push_back(i);
+      else rest.push_back(i);
+    }
+    if ((int)pc.members.size() < min_cover && !passes.empty()) {
+      // not worth a pass of its own (a pass re-reads psi and read-modify-writes y)
+      for (int i : uncovered) remote.push_back(i);
+      uncovered.clear();
+      break;
+    }
+    passes.push_back(std::move(pc));
+    uncovered.swap(rest);
+  }
+  if (passes.empty()) {
+    PassChoice pc;
+    pc.free_mask = fill_mask(low) & all;
+    passes.push_back(pc);
+  }
+  for (int i : remote) passes[0].members.push_back(i);
+  return passes;
+}
+
+// Build the device-facing arrays of one pass.
+inline PassHost build_pass(const std::vector<CompTerm>& comp,
+                           const std::vector<std::vector<int>>& terms_of_mask,
+                           const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc) {
+  PassHost P;
+  P.free_mask = pc.free_mask;
+  P.L = popc64(pc.free_mask);
+  const uint64_t S = pc.free_mask;
+  struct Key {
+    uint8_t im;
+    uint32_t zt;
+    int term;
+  };
+  ChunkRec cur{0, 0, 0, 0};
+  auto flush_chunk = [&]() {
+    if (cur.ng > 0) P.chunks.push_back(cur);
+    cur.g0 += cur.ng;
+    cur.p0 += cur.np;
+    cur.ng = 0;
+    cur.np = 0;
+  };
+  P.pat_tptr.push_back(0);
+  for (int mi : pc.members) {
+    const uint64_t xl = masks[mi];
+    const bool remote = (xl & ~S) != 0;
+    P.n_xgroups++;
+    if (remote) P.n_remote++;
+    std::vector<Key> keys;
+    keys.reserve(terms_of_mask[mi].size());
+    for (int t : terms_of_mask[mi])
+      keys.push_back({comp[t].im, (uint32_t)pext64(comp[t].zl, S), t});
+    auto cls_of = [](const Key& k) { return (int)k.im * 8 + (int)((k.zt >> kRegBitLo) & 7); };
+    std::stable_sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
+      int ca = cls_of(a), cb = cls_of(b);
+      if (ca != cb) return ca < cb;
+      return a.zt < b.zt;
+    });
+    // patterns = runs of equal (im, zt)
+    struct Pat { int cls; uint32_t zt; int k0, k1; };
+    std::vector<Pat> pats;
+    for (int k = 0; k < (int)keys.size();) {
+      int e = k;
+      while (e < (int)keys.size() && keys[e].im == keys[k].im && keys[e].zt == keys[k].zt) ++e;
+      pats.push_back({cls_of(keys[k]), keys[k].zt, k, e});
+      k = e;
+    }
+    // emit sub-groups: each holds <= kPatChunk patterns and <= 255 patterns per class.
+    // A sub-group must keep class order, so cut greedily in pattern order.
+    size_t p = 0;
+    while (p < pats.size()) {
+      GroupRec G;
+      std::memset(&G, 0, sizeof(G));
+      G.xt = (uint32_t)pext64(xl, S) | (remote ? 0x80000000u : 0u);
+      G.xl = xl;
+      int count = 0;
+      size_t q = p;
+      while (q < pats.size() && count < kPatChunk && G.cnt[pats[q].cls] < 255) {
+        G.cnt[pats[q].cls]++;
+        ++count;
+        ++q;
+      }
+      if (cur.ng + 1 > kGrpChunk || cur.np + count > kPatChunk) flush_chunk();
+      G.pat0 = (uint32_t)cur.np;
+      for (size_t j = p; j < q; ++j) {
+        P.pat_zt.push_back((uint16_t)pats[j].zt);
+        for (int k = pats[j].k0; k < pats[j].k1; ++k) {
+          const CompTerm& ct = comp[keys[k].term];
+          P.term_zb.push_back(ct.zl & ~S);
+          P.term_val.push_back(ct.val);
+        }
+        P.pat_tptr.push_back((uint32_t)P.term_val.size());
+      }
+      P.groups.push_back(G);
+      cur.ng++;
+      cur.np += count;
+      p = q;
+    }
+  }
+  flush_chunk();
+  (void)n_loc;
+  return P;
+}
+
+// Split merged terms into parts by global x-part for (rank, world) and plan each part.
+inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, int n, int p_bits,
+                                         int rank, const PlanOptions& opt) {
+  const int n_loc = n - p_bits;
+  const uint64_t lm = low_mask(n_loc);
+  std::map<int, PartHost> parts;
+  for (const auto& t : terms) {
+    int g = p_bits ? (int)(t.x >> n_loc) : 0;
+    uint64_t zg = p_bits ? (t.z >> n_loc) : 0;
+    double sgn = (popc64((uint64_t)rank & zg) & 1) ? -1.0 : 1.0;
+    PartHost& P = parts[g];
+    P.g = g;
+    if (t.re != 0.0) P.comp.push_back({t.x & lm, t.z & lm, sgn * t.re, 0});
+    if (t.im != 0.0) P.comp.push_back({t.x & lm, t.z & lm, sgn * t.im, 1});
+  }
+  std::vector<PartHost> out;
+  for (auto& kv : parts) {
+    PartHost& P = kv.second;
+    // distinct local x masks, sorted: diagonal first, then by value
+    std::map<uint64_t, int> idx;
+    std::vector<uint64_t> masks;
+    std::vector<std::vector<int>> tom;
+    for (int t = 0; t < (int)P.comp.size(); ++t) {
+      auto it = idx.find(P.comp[t].xl);
+      if (it == idx.end()) {
+        it = idx.emplace(P.comp[t].xl, (int)masks.size()).first;
+        masks.push_back(P.comp[t].xl);
+        tom.emplace_back();
+      }
+      tom[it->second].push_back(t);
+    }
+    P.n_xgroups = (int64_t)masks.size();
+    // streaming plan (kernel A): merge re/im components of the same (x,z) back to complex
+    {
+      std::vector<int> order(masks.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return masks[a] < masks[b]; });
+      for (int mi : order) {
+        SimpleGroup sg{masks[mi], (int32_t)P.sterms.size(), 0};
+        std::map<uint64_t, int> zidx;
+        for (int t : tom[mi]) {
+          auto it = zidx.find(P.comp[t].zl);
+          if (it == zidx.end()) {
+            it = zidx.emplace(P.comp[t].zl, (int)P.sterms.size()).first;
+            P.sterms.push_back({P.comp[t].zl, 0.0, 0.0});
+          }
+          if (P.comp[t].im) P.sterms[it->second].im += P.comp[t].val;
+          else P.sterms[it->second].re += P.comp[t].val;
+        }
+        sg.nt = (int32_t)P.sterms.size() - sg.t0;
+        P.sgroups.push_back(sg);
+      }
+    }
+    // tiled plan (kernel B)
+    if (n_loc >= 11 && opt.kernel != 1) {
+      int L = std::max(11, std::min({opt.tile_bits, kMaxTileBits, n_loc}));
+      std::vector<PassChoice> pcs = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover);
+      for (auto& pc : pcs) P.passes.push_back(build_pass(P.comp, tom, masks, pc, n_loc));
+    }
+    out.push_back(std::move(P));
+  }
+  return out;
+}
+
+}  // namespace psum
