@@ -67,6 +67,39 @@ void psum_oracle_apply(int n, int64_t T, const uint64_t* x, const uint64_t* z, c
   double* cre = (double*)malloc(sizeof(double) * (size_t)(T > 0 ? T : 1));
   double* cim = (double*)malloc(sizeof(double) * (size_t)(T > 0 ? T : 1));
   for (int64_t k = 0; k < T; ++k) phase_coeff(coeff, ypow, k, &cre[k], &cim[k]);
+  const uint64_t B = 4096; /* rows per block: the block's y stays in L2 while terms stream by */
+  if (row_begin % B == 0 && row_end % B == 0 && row_end > row_begin) {
+    /* term-outer, row-block-inner order: for a fixed term the partner amplitudes i^x of an
+       aligned block form one contiguous aligned block, so memory is streamed, not gathered.
+       Per row the sum over k runs in the same order as the row-major loop below. */
+    const int64_t nblk = (int64_t)((row_end - row_begin) / B);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < nblk; ++b) {
+      const uint64_t base = row_begin + (uint64_t)b * B;
+      double* yb = y + 2 * ((uint64_t)b * B);
+      for (uint64_t t = 0; t < 2 * B; ++t) yb[t] = 0.0;
+      for (int64_t k = 0; k < T; ++k) {
+        const uint64_t xk = x[k], zk = z[k];
+        const double cr = cre[k], ci = cim[k];
+        const double* pb = psi + 2 * ((base ^ xk) & ~(B - 1));
+        const uint64_t xl = xk & (B - 1);
+        const int pbase = parity64(base & zk);
+        const uint64_t zl = zk & (B - 1);
+        for (uint64_t t = 0; t < B; ++t) {
+          const uint64_t j = t ^ xl;
+          const double pr = pb[2 * j], pi = pb[2 * j + 1];
+          double tr = cr * pr - ci * pi;
+          double ti = cr * pi + ci * pr;
+          if (pbase ^ parity64(t & zl)) { tr = -tr; ti = -ti; }
+          yb[2 * t] += tr;
+          yb[2 * t + 1] += ti;
+        }
+      }
+    }
+    free(cre);
+    free(cim);
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for (int64_t r = (int64_t)row_begin; r < (int64_t)row_end; ++r) {
     const uint64_t i = (uint64_t)r;

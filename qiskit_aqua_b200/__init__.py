@@ -7,3 +7,9 @@ from ._lib import PsumError, lib  # noqa: F401
 from .engine import PauliSumEngine, fill_state, nccl_unique_id, pack_masks  # noqa: F401
 
 __version__ = '0.1.0'
+from .operators import (AquaError, ComposedOp, I, ListOp, MatrixExpectation, OperatorStateFn,  # noqa: F401,E402
+                        Pauli, PauliOp, StateFn, SummedOp, VectorStateFn, WeightedPauliOperator,
+                        X, Y, Z)
+from .algorithms import (EigensolverResult, MinimumEigensolverResult, NumPyEigensolver,  # noqa: F401,E402
+                         NumPyMinimumEigensolver)
+from .applications import FermionicOperator, max_cut, random_graph, sample_most_likely  # noqa: F401,E402
