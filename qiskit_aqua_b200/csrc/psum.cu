@@ -153,7 +153,7 @@ static int plan(psum_handle_s* h) {
 }
 
 static size_t pass_smem_bytes(int L) {
-  return ((size_t)16 << L) + 8 * kPatChunk + 8 * 32 + sizeof(GroupRec) * kGrpChunk + 2 * kPatChunk +
+  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * kGrpChunk +
          16 * (kThreads / 32);
 }
 

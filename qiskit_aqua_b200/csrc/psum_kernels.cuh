@@ -95,6 +95,15 @@ __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
 //   EXPECT: accumulate sum conj(bra_i) * contribution_i into partial[blockIdx.x]
 //   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
 // ------------------------------------------------------------------------------------------
+// D[(C >> 3) * 8 + r] += (-1)^{popc(r & C)} s  for r = 0..7, with C a compile-time class
+#define PSUM_CLASS_CASE(C)                                    \
+  case C: {                                                   \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) {           \
+      if (__popc(r & (C & 7)) & 1) D[((C) >> 3) * 8 + r] -= s; \
+      else D[((C) >> 3) * 8 + r] += s;                        \
+    }                                                         \
+  } break;
+
 template <bool STORE, bool EXPECT>
 __global__ void __launch_bounds__(kThreads, 2)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
@@ -103,11 +112,10 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   const int L = P.L;
   const uint32_t tile_amps = 1u << L;
   double2* tile = reinterpret_cast<double2*>(smem_raw);
-  double* cf = reinterpret_cast<double*>(tile + tile_amps);
-  uint64_t* offHi = reinterpret_cast<uint64_t*>(cf + kPatChunk);
+  PatRec* pat = reinterpret_cast<PatRec*>(tile + tile_amps);
+  uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
   GroupRec* grp = reinterpret_cast<GroupRec*>(offHi + 32);
-  uint16_t* zts = reinterpret_cast<uint16_t*>(grp + kGrpChunk);
-  double2* red = reinterpret_cast<double2*>(zts + kPatChunk);
+  double2* red = reinterpret_cast<double2*>(grp + kGrpChunk);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -147,49 +155,51 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 
       for (int c = 0; c < P.nchunks; ++c) {
         const ChunkRec ch = P.chunks[c];
-        __syncthreads();  // everyone is done with the previous chunk's cf / grp / zts
+        __syncthreads();  // everyone is done with the previous chunk's pat / grp
+        // fold: bits outside the free set become a per-tile sign of each term; equal in-tile
+        // patterns of a group are summed into one coefficient
         for (int p = tid; p < ch.np; p += kThreads) {
           const int gp = ch.p0 + p;
           const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
           double v = 0.0;
           for (uint32_t t = ta; t < tb; ++t)
             v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
-          cf[p] = v;
-          zts[p] = P.pat_zt[gp];
+          PatRec pr;
+          pr.cf = v;
+          pr.zt = P.pat_zt[gp];
+          pr.pad = 0;
+          *reinterpret_cast<uint4*>(&pat[p]) = *reinterpret_cast<uint4*>(&pr);
         }
         for (int g = tid; g < ch.ng * 2; g += kThreads)
-          reinterpret_cast<uint4*>(grp)[g] =
-              reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
+          reinterpret_cast<uint4*>(grp)[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
         __syncthreads();
 
         for (int g = 0; g < ch.ng; ++g) {
-          const uint4 hdr = reinterpret_cast<const uint4*>(grp)[2 * g];
-          const uint4 cw = reinterpret_cast<const uint4*>(grp)[2 * g + 1];
-          const uint32_t xt = hdr.x & 0x7fffffffu;
-          const bool remote = (hdr.x >> 31) != 0;
-          int p = (int)hdr.y;
-          const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w};
-          double S[16];
+          const uint4 h0 = reinterpret_cast<const uint4*>(grp)[2 * g];
+          const uint2 h1 = reinterpret_cast<const uint2*>(grp)[4 * g + 2];
+          const uint32_t xt = h0.x & 0x7fffffffu;
+          const bool remote = (h0.x >> 31) != 0;
+          int p = (int)(h0.y & 0xffffu);
+          const int nent = (int)((h0.y >> 16) & 7u);
+          const bool has_im = ((h0.y >> 20) & 1u) != 0;
+          uint64_t ents = (uint64_t)h1.x | ((uint64_t)h1.y << 32);
+          double D[16];
 #pragma unroll
-          for (int cls = 0; cls < 16; ++cls) {
-            S[cls] = 0.0;
-            const int cnt = (int)((cwv[cls >> 2] >> (8 * (cls & 3))) & 255u);
-            for (int j = 0; j < cnt; ++j, ++p)
-              S[cls] += flip_sign(cf[p], __popc((uint32_t)zts[p] & t0) & 1);
-          }
-          const bool has_im = (cw.z | cw.w) != 0u;
-          const bool re_flat = (cw.x <= 255u) && cw.y == 0u;  // only class 0 populated
-          const bool im_flat = (cw.z <= 255u) && cw.w == 0u;
-          if (!re_flat) wht8(S);
-          else {
-#pragma unroll
-            for (int r = 1; r < 8; ++r) S[r] = S[0];
-          }
-          if (has_im) {
-            if (!im_flat) wht8(S + 8);
-            else {
-#pragma unroll
-              for (int r = 1; r < 8; ++r) S[8 + r] = S[8];
+          for (int r = 0; r < 16; ++r) D[r] = 0.0;
+          for (int e = 0; e < nent; ++e) {
+            const uint32_t ent = (uint32_t)ents & 0xffffu;
+            ents >>= 16;
+            const int cnt = (int)(ent & 0xfffu);
+            double s = 0.0;
+            for (int j = 0; j < cnt; ++j, ++p) {
+              const uint4 rec = reinterpret_cast<const uint4*>(pat)[p];
+              s += __hiloint2double((int)(rec.y ^ ((uint32_t)(__popc(rec.z & t0)) << 31)), (int)rec.x);
+            }
+            switch (ent >> 12) {
+              PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
+              PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
+              PSUM_CLASS_CASE(8) PSUM_CLASS_CASE(9) PSUM_CLASS_CASE(10) PSUM_CLASS_CASE(11)
+              PSUM_CLASS_CASE(12) PSUM_CLASS_CASE(13) PSUM_CLASS_CASE(14) PSUM_CLASS_CASE(15)
             }
           }
           double2 pv[8];
@@ -198,7 +208,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
             for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
           } else {
-            const uint64_t ip = i0 ^ ((uint64_t)hdr.z | ((uint64_t)hdr.w << 32));
+            const uint64_t ip = i0 ^ ((uint64_t)h0.z | ((uint64_t)h0.w << 32));
 #pragma unroll
             for (int r = 0; r < 8; ++r)
               pv[r] = __ldg(&src[ip ^ ((r & 1) ? b5 : 0ull) ^ ((r & 2) ? b6 : 0ull) ^
@@ -207,14 +217,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           if (has_im) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              yacc[r].x += S[r] * pv[r].x - S[8 + r] * pv[r].y;
-              yacc[r].y += S[r] * pv[r].y + S[8 + r] * pv[r].x;
+              yacc[r].x += D[r] * pv[r].x - D[8 + r] * pv[r].y;
+              yacc[r].y += D[r] * pv[r].y + D[8 + r] * pv[r].x;
             }
           } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              yacc[r].x += S[r] * pv[r].x;
-              yacc[r].y += S[r] * pv[r].y;
+              yacc[r].x += D[r] * pv[r].x;
+              yacc[r].y += D[r] * pv[r].y;
             }
           }
         }
@@ -245,6 +255,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     if (tid == 0) partial[blockIdx.x] = tot;
   }
 }
+#undef PSUM_CLASS_CASE
 
 // ------------------------------------------------------------------------------------------
 // Kernel A: streaming form, one amplitude per thread (grid-stride).  Any n_loc >= 0.

@@ -40,13 +40,21 @@ struct CompTerm {  // real-valued component term of one shard/part: value * (im 
 };
 
 // ---- device-facing records (layout shared with the kernels) --------------------------------
-struct GroupRec {    // 32 bytes
-  uint32_t xt;       // tile-local xor (compressed free-set bits of x); bit31 = remote flag
-  uint32_t pat0;     // first pattern, relative to the chunk's first pattern
-  uint64_t xl;       // full local x mask (partner index = i ^ xl)
-  uint8_t cnt[16];   // patterns per class: cls = im*8 + ((zt >> 5) & 7)
+struct GroupRec {     // 32 bytes
+  uint32_t xt;        // tile-local xor (compressed free-set bits of x); bit31 = remote flag
+  uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
+                      // bit 20 = has imaginary patterns
+  uint64_t xl;        // full local x mask (partner index = i ^ xl)
+  uint16_t ent[4];    // non-empty classes: (cls << 12) | count ; cls = im*8 + ((zt >> 5) & 7)
+  uint64_t pad;
 };
 static_assert(sizeof(GroupRec) == 32, "GroupRec layout");
+
+struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is written by the fold)
+  double cf;
+  uint32_t zt;
+  uint32_t pad;
+};
 
 struct ChunkRec {  // 16 bytes
   int32_t g0, ng, p0, np;
@@ -250,23 +258,32 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       pats.push_back({cls_of(keys[k]), keys[k].zt, k, e});
       k = e;
     }
-    // emit sub-groups: each holds <= kPatChunk patterns and <= 255 patterns per class.
-    // A sub-group must keep class order, so cut greedily in pattern order.
+    // emit sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 4095
+    // patterns per class.  Patterns are in class order, so cut greedily.
     size_t p = 0;
     while (p < pats.size()) {
       GroupRec G;
       std::memset(&G, 0, sizeof(G));
       G.xt = (uint32_t)pext64(xl, S) | (remote ? 0x80000000u : 0u);
       G.xl = xl;
-      int count = 0;
+      int count = 0, nent = 0;
+      bool has_im = false;
       size_t q = p;
-      while (q < pats.size() && count < kPatChunk && G.cnt[pats[q].cls] < 255) {
-        G.cnt[pats[q].cls]++;
+      while (q < pats.size() && count < kPatChunk) {
+        const int cls = pats[q].cls;
+        if (nent == 0 || (G.ent[nent - 1] >> 12) != cls) {
+          if (nent == 4) break;
+          G.ent[nent++] = (uint16_t)(cls << 12);
+        } else if ((G.ent[nent - 1] & 0xfff) == 0xfff) {
+          break;
+        }
+        G.ent[nent - 1]++;
+        if (cls >= 8) has_im = true;
         ++count;
         ++q;
       }
       if (cur.ng + 1 > kGrpChunk || cur.np + count > kPatChunk) flush_chunk();
-      G.pat0 = (uint32_t)cur.np;
+      G.meta = (uint32_t)cur.np | ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u);
       for (size_t j = p; j < q; ++j) {
         P.pat_zt.push_back((uint16_t)pats[j].zt);
         for (int k = pats[j].k0; k < pats[j].k1; ++k) {
