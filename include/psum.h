@@ -56,7 +56,8 @@ int psum_set_option(psum_handle_t h, const char* key, int64_t value);
 
 /* info[0]=n_qubits [1]=merged terms [2]=distinct x-masks (G_x) [3]=passes [4]=groups read from
  * global memory ("remote") [5]=is_hermitian [6]=is_diagonal [7]=local qubits [8]=sum of patterns
- * [9]=component terms [10]=tile_bits [11]=distinct non-zero global x-parts */
+ * [9]=component terms [10]=tile_bits [11]=distinct non-zero global x-parts [12]=flat groups
+ * [13]=group records (x-groups after class splitting) */
 int psum_info(psum_handle_t h, int64_t* info, int n_info);
 /* Free-bit set (bit mask over local qubits) and group count of pass p of global part g. */
 int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* n_groups,
@@ -116,10 +117,11 @@ int psum_nccl_unique_id(void* out128);
 int psum_shard_init(psum_handle_t h, int rank, int world, const void* unique_id128);
 /* Contribution of the terms whose global x-part is g (0 <= g < world) to this rank's y, reading
  * partner amplitudes from src_dev (= the shard of rank r^g; g == 0 -> the local shard).
- * accumulate != 0 adds into y_dev.  expect_acc (host, 2 doubles, may be NULL) += sum conj(bra) y
- * with bra_dev = this rank's own shard. */
+ * accumulate != 0 adds into y_dev.  expect_out (host, 2 doubles, may be NULL), bra_dev = this
+ * rank's own shard: with y_dev it receives sum conj(bra) y of y AFTER this call (so the call for
+ * the last part yields the total); with y_dev == NULL it receives this part's contribution. */
 int psum_apply_part(psum_handle_t h, int g, const void* src_dev, const void* bra_dev, void* y_dev,
-                    int accumulate, double* expect_acc, psum_stream_t stream);
+                    int accumulate, double* expect_out, psum_stream_t stream);
 /* Component terms this rank applies for global part g (rank sign folded in): for CPU-side
  * checks of the sharding algebra.  Arrays of capacity cap; returns the count in *n_out. */
 int psum_shard_terms(psum_handle_t h, int g, int64_t cap, uint64_t* x_local, uint64_t* z_local,

@@ -96,6 +96,7 @@ int load_nccl() {
 // ---------------------------------------------------------------------------------------------
 struct DevPass {
   PassParams params;
+  bool has_im = false;
   int grid = 0;
   size_t smem = 0;
 };
@@ -214,11 +215,11 @@ static int upload(psum_handle_s* h) {
         dp.params.L = ph.L;
         dp.params.n_nonfree = h->n_loc - ph.L;
         dp.params.ntiles = 1ull << (h->n_loc - ph.L);
-        int fj = 0, nj = 0;
-        for (int b = 0; b < h->n_loc; ++b) {
-          if (ph.free_mask >> b & 1ull) dp.params.fbit[fj++] = (uint8_t)b;
-          else dp.params.nbit[nj++] = (uint8_t)b;
-        }
+        int nj = 0;
+        for (int b = 0; b < h->n_loc; ++b)
+          if (!(ph.free_mask >> b & 1ull)) dp.params.nbit[nj++] = (uint8_t)b;
+        for (int j = 0; j < ph.L; ++j) dp.params.fbit[j] = ph.fbit[j];
+        dp.has_im = ph.has_im;
         dp.smem = pass_smem_bytes(ph.L);
         int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
         dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
@@ -243,9 +244,11 @@ static int upload(psum_handle_s* h) {
   static bool attr_done = false;
   if (!attr_done) {
     int max_smem = (int)pass_smem_bytes(kMaxTileBits);
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define SET_SMEM(S, E, I) \
+  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SET_SMEM(true, true, true) SET_SMEM(true, true, false) SET_SMEM(true, false, true)
+    SET_SMEM(true, false, false) SET_SMEM(false, true, true) SET_SMEM(false, true, false)
+#undef SET_SMEM
     attr_done = true;
   }
   h->uploaded = true;
@@ -323,7 +326,7 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
 extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
   if (!h || !info) return fail(PSUM_ERR_INVALID, "null argument");
   if (!h->planned) PS_TRY(plan(h));
-  int64_t v[12] = {0};
+  int64_t v[16] = {0};
   v[0] = h->n;
   v[1] = (int64_t)h->terms.size();
   {
@@ -338,6 +341,8 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
     for (auto& ps : P.passes) {
       v[4] += ps.n_remote;
       v[8] += (int64_t)ps.pat_zt.size();
+      v[12] += ps.n_flat;
+      v[13] += (int64_t)ps.groups.size();
       v[10] = ps.L;
     }
     v[9] += (int64_t)P.comp.size();
@@ -347,7 +352,7 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
   v[6] = h->diagonal;
   v[7] = h->n_loc;
   v[11] = gparts;
-  for (int i = 0; i < n_info && i < 12; ++i) info[i] = v[i];
+  for (int i = 0; i < n_info && i < 16; ++i) info[i] = v[i];
   return PSUM_OK;
 }
 
@@ -374,32 +379,45 @@ extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask
 // ---------------------------------------------------------------------------------------------
 // launch sequencing
 // ---------------------------------------------------------------------------------------------
-// Runs one part.  Expectation partials are appended at d_partial[*pcount...].
+// Runs one part.  With a y buffer every pass accumulates into y and only the launch flagged
+// `last` reduces <bra|y> over the FINAL y; without y each pass appends the partials of its own
+// contribution at d_partial[*pcount...].
 static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, const double2* bra,
-                    double2* y, int accumulate, bool want_expect, size_t* pcount, cudaStream_t st) {
+                    double2* y, int accumulate, bool want_expect, bool last_part, size_t* pcount,
+                    cudaStream_t st) {
   const bool bra_is_src = (bra == src) || bra == nullptr;
   if (!D.passes.empty()) {
-    bool first = true;
-    for (const DevPass& dp : D.passes) {
+    for (size_t pi = 0; pi < D.passes.size(); ++pi) {
+      const DevPass& dp = D.passes[pi];
       PassParams pp = dp.params;
-      pp.accumulate = (accumulate || !first) ? 1 : 0;
-      double2* part = want_expect ? h->d_partial + *pcount : nullptr;
+      pp.accumulate = (accumulate || pi > 0) ? 1 : 0;
+      const bool last = last_part && (pi + 1 == D.passes.size());
+      const bool ex = want_expect && (y ? last : true);
+      double2* part = ex ? h->d_partial + *pcount : nullptr;
       const double2* b = bra_is_src ? nullptr : bra;
-      if (want_expect && *pcount + dp.grid > h->partial_cap)
+      if (ex && *pcount + dp.grid > h->partial_cap)
         return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
-      if (y && want_expect) k_pass<true, true><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
-      else if (y) k_pass<true, false><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
-      else k_pass<false, true><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part);
-      if (want_expect) *pcount += dp.grid;
-      first = false;
+#define LAUNCH(S, E, I) k_pass<S, E, I><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part)
+      if (dp.has_im) {
+        if (y && ex) LAUNCH(true, true, true);
+        else if (y) LAUNCH(true, false, true);
+        else LAUNCH(false, true, true);
+      } else {
+        if (y && ex) LAUNCH(true, true, false);
+        else if (y) LAUNCH(true, false, false);
+        else LAUNCH(false, true, false);
+      }
+#undef LAUNCH
+      if (ex) *pcount += dp.grid;
     }
   } else {
-    double2* part = want_expect ? h->d_partial + *pcount : nullptr;
-    if (want_expect && *pcount + D.grid_stream > h->partial_cap)
+    const bool ex = want_expect && (y ? last_part : true);
+    double2* part = ex ? h->d_partial + *pcount : nullptr;
+    if (ex && *pcount + D.grid_stream > h->partial_cap)
       return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
     k_stream<<<D.grid_stream, kThreads, 0, st>>>(src, bra ? bra : src, y, D.sgroups, D.nsg, D.sterms,
                                                  n_local_amps(h), accumulate, part);
-    if (want_expect) *pcount += D.grid_stream;
+    if (ex) *pcount += D.grid_stream;
   }
   CUDA_TRY(cudaGetLastError());
   return PSUM_OK;
@@ -424,7 +442,7 @@ static int apply_local(psum_handle_s* h, const double2* psi, const double2* bra,
   PS_TRY(upload(h));
   size_t pcount = 0;
   for (const DevPart& D : h->dparts)
-    PS_TRY(run_part(h, D, psi, bra, y, 0, expect_out != nullptr, &pcount, st));
+    PS_TRY(run_part(h, D, psi, bra, y, 0, expect_out != nullptr, &D == &h->dparts.back(), &pcount, st));
   if (expect_out) {
     k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
     CUDA_TRY(cudaGetLastError());
@@ -465,7 +483,7 @@ extern "C" int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev
   for (int b = 0; b < batch; ++b) {
     const double2* psi = base + (uint64_t)b * n_local_amps(h);
     size_t pcount = 0;
-    for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, &pcount, st));
+    for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st));
     stride_partials = pcount;
     k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar + b, 0);
   }
@@ -675,14 +693,14 @@ extern "C" int psum_apply_part(psum_handle_t h, int g, const void* src_dev, cons
   }
   size_t pcount = 0;
   const double2* bra = bra_dev ? (const double2*)bra_dev : (const double2*)src_dev;
-  PS_TRY(run_part(h, *D, (const double2*)src_dev, bra, (double2*)y_dev, accumulate, expect_acc != nullptr, &pcount, st));
+  PS_TRY(run_part(h, *D, (const double2*)src_dev, bra, (double2*)y_dev, accumulate, expect_acc != nullptr, true, &pcount, st));
   if (expect_acc) {
     double v[2];
     k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
     CUDA_TRY(cudaGetLastError());
     PS_TRY(fetch_scalars(h, 1, v, st));
-    expect_acc[0] += v[0];
-    expect_acc[1] += v[1];
+    expect_acc[0] = v[0];
+    expect_acc[1] = v[1];
   }
   return PSUM_OK;
 }
@@ -750,7 +768,7 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
   if (!remote.empty()) PS_TRY(post_exchange(remote[0], 0, false));
   for (auto& D : h->dparts)
     if (D.g == 0) {
-      PS_TRY(run_part(h, D, psi, psi, y, 0, expect_out != nullptr, &pcount, st));
+      PS_TRY(run_part(h, D, psi, psi, y, 0, expect_out != nullptr, remote.empty(), &pcount, st));
       wrote_y = true;
     }
   if (!wrote_y && y) CUDA_TRY(cudaMemsetAsync(y, 0, N * sizeof(double2), st));
@@ -763,7 +781,7 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
     }
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_recv[slot], 0));
     const double2* buf = (const double2*)recv_dev + (uint64_t)slot * N;
-    PS_TRY(run_part(h, *remote[r], buf, psi, y, 1, expect_out != nullptr, &pcount, st));
+    PS_TRY(run_part(h, *remote[r], buf, psi, y, 1, expect_out != nullptr, r + 1 == remote.size(), &pcount, st));
     CUDA_TRY(cudaEventRecord(h->ev_used[slot], st));
     used_once[slot] = true;
     if (nbuf == 1 && r + 1 < remote.size()) PS_TRY(post_exchange(remote[r + 1], 0, true));

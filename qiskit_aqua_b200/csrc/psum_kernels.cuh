@@ -9,8 +9,10 @@
 // Signs are never evaluated per (term, amplitude):
 //   * bits outside S:   folded into the coefficient once per (tile, term)      ("fold")
 //   * equal in-tile z-patterns of one group are merged into one pattern          ("compaction")
-//   * tile bits 5..7 (the 8 amplitudes a thread owns): patterns are summed per class
-//     zr = (zt >> 5) & 7 and an 8-point Walsh-Hadamard butterfly expands them    ("class sums")
+//   * tile bits 5..7 (the 8 amplitudes a thread owns, chosen by the planner among the free
+//     qubits the pass's z-masks touch least): patterns are summed per class zr = (zt >> 5) & 7
+//     and added with compile-time signs; a group whose patterns are all class 0 ("flat") has
+//     one D for the 8 amplitudes                                                ("class sums")
 //   * the remaining tile bits: one popc per (pattern, thread)
 // Kernel A (k_stream) is the plain streaming form used for n_loc < 11 qubits.
 #pragma once
@@ -91,20 +93,35 @@ __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
 
 // ------------------------------------------------------------------------------------------
 // Kernel B: one pass over all tiles of a free set.
-//   STORE : write / accumulate y
-//   EXPECT: accumulate sum conj(bra_i) * contribution_i into partial[blockIdx.x]
-//   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
 // ------------------------------------------------------------------------------------------
 // D[(C >> 3) * 8 + r] += (-1)^{popc(r & C)} s  for r = 0..7, with C a compile-time class
-#define PSUM_CLASS_CASE(C)                                    \
-  case C: {                                                   \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) {           \
-      if (__popc(r & (C & 7)) & 1) D[((C) >> 3) * 8 + r] -= s; \
-      else D[((C) >> 3) * 8 + r] += s;                        \
-    }                                                         \
+#define PSUM_CLASS_CASE(C)                                       \
+  case C: {                                                      \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) {              \
+      if (__popc(r & ((C) & 7)) & 1) D[((C) >> 3) * 8 + r] -= s; \
+      else D[((C) >> 3) * 8 + r] += s;                           \
+    }                                                            \
   } break;
 
-template <bool STORE, bool EXPECT>
+// sum of the (tile-folded, thread-signed) coefficients of `cnt` patterns starting at p
+__device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, int& p, int cnt, uint32_t t0) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < cnt; ++j, ++p) {
+    const uint4 rec = pat4[p];
+    s += __hiloint2double((int)(rec.y ^ ((uint32_t)(__popc(rec.z & t0)) << 31)), (int)rec.x);
+  }
+  return s;
+}
+
+//   STORE : y (+)= contribution.  With `accumulate` the accumulators start from the old y, so a
+//           pass costs one read and one write of y and the last pass sees the final H.psi
+//   EXPECT: STORE mode  -> sum conj(bra_i) * y_i of the FINAL y (host enables it on the last
+//                          launch only);  no-STORE mode -> sum conj(bra_i) * contribution_i
+//   IM    : the pass has imaginary component patterns (complex D); real-only passes carry half
+//           the class accumulators
+//   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
+template <bool STORE, bool EXPECT, bool IM>
 __global__ void __launch_bounds__(kThreads, 2)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
        const PassParams P, double2* __restrict__ partial) {
@@ -116,6 +133,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
   GroupRec* grp = reinterpret_cast<GroupRec*>(offHi + 32);
   double2* red = reinterpret_cast<double2*>(grp + kGrpChunk);
+  const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -133,8 +151,29 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   const uint64_t b5 = 1ull << P.fbit[5], b6 = 1ull << P.fbit[6], b7 = 1ull << P.fbit[7];
   const int nrounds = (int)(tile_amps / kRoundAmps);
   const int nload = (int)(tile_amps / kThreads);
+  const bool one_chunk = (P.nchunks == 1);
 
   double2 eacc = make_double2(0.0, 0.0);
+
+  // fold: bits outside the free set become a per-tile sign of each term; equal in-tile patterns
+  // of a group are summed into one coefficient.  Also stages the chunk's group records.
+  auto stage_chunk = [&](const ChunkRec ch, uint64_t base) {
+    for (int p = tid; p < ch.np; p += kThreads) {
+      const int gp = ch.p0 + p;
+      const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
+      double v = 0.0;
+      for (uint32_t t = ta; t < tb; ++t)
+        v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+      uint4 rec;
+      rec.x = (uint32_t)__double2loint(v);
+      rec.y = (uint32_t)__double2hiint(v);
+      rec.z = P.pat_zt[gp];
+      rec.w = 0;
+      reinterpret_cast<uint4*>(pat)[p] = rec;
+    }
+    for (int g = tid; g < ch.ng * 2; g += kThreads)
+      reinterpret_cast<uint4*>(grp)[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
+  };
 
   for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
     uint64_t base = 0;
@@ -143,6 +182,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     __syncthreads();  // previous tile fully consumed; offHi visible on the first trip
     for (int j = 0; j < nload; ++j)
       cp_async16(&tile[j * kThreads + tid], &src[base | offLo8 | offHi[j]]);
+    if (one_chunk) stage_chunk(P.chunks[0], base);  // overlaps the tile load
     cp_async_wait_all();
     __syncthreads();
 
@@ -151,57 +191,24 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       const uint64_t i0 = base | offLane | offHi[rnd * 8 + warp];
       double2 yacc[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) yacc[r] = make_double2(0.0, 0.0);
+      for (int r = 0; r < 8; ++r) {
+        const uint64_t ir = i0 | ((r & 1) ? b5 : 0ull) | ((r & 2) ? b6 : 0ull) | ((r & 4) ? b7 : 0ull);
+        yacc[r] = (STORE && P.accumulate) ? y[ir] : make_double2(0.0, 0.0);
+      }
 
       for (int c = 0; c < P.nchunks; ++c) {
         const ChunkRec ch = P.chunks[c];
-        __syncthreads();  // everyone is done with the previous chunk's pat / grp
-        // fold: bits outside the free set become a per-tile sign of each term; equal in-tile
-        // patterns of a group are summed into one coefficient
-        for (int p = tid; p < ch.np; p += kThreads) {
-          const int gp = ch.p0 + p;
-          const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
-          double v = 0.0;
-          for (uint32_t t = ta; t < tb; ++t)
-            v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
-          PatRec pr;
-          pr.cf = v;
-          pr.zt = P.pat_zt[gp];
-          pr.pad = 0;
-          *reinterpret_cast<uint4*>(&pat[p]) = *reinterpret_cast<uint4*>(&pr);
+        if (!one_chunk) {
+          __syncthreads();  // everyone is done with the previous chunk's pat / grp
+          stage_chunk(ch, base);
+          __syncthreads();
         }
-        for (int g = tid; g < ch.ng * 2; g += kThreads)
-          reinterpret_cast<uint4*>(grp)[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
-        __syncthreads();
 
         for (int g = 0; g < ch.ng; ++g) {
           const uint4 h0 = reinterpret_cast<const uint4*>(grp)[2 * g];
-          const uint2 h1 = reinterpret_cast<const uint2*>(grp)[4 * g + 2];
           const uint32_t xt = h0.x & 0x7fffffffu;
           const bool remote = (h0.x >> 31) != 0;
           int p = (int)(h0.y & 0xffffu);
-          const int nent = (int)((h0.y >> 16) & 7u);
-          const bool has_im = ((h0.y >> 20) & 1u) != 0;
-          uint64_t ents = (uint64_t)h1.x | ((uint64_t)h1.y << 32);
-          double D[16];
-#pragma unroll
-          for (int r = 0; r < 16; ++r) D[r] = 0.0;
-          for (int e = 0; e < nent; ++e) {
-            const uint32_t ent = (uint32_t)ents & 0xffffu;
-            ents >>= 16;
-            const int cnt = (int)(ent & 0xfffu);
-            double s = 0.0;
-            for (int j = 0; j < cnt; ++j, ++p) {
-              const uint4 rec = reinterpret_cast<const uint4*>(pat)[p];
-              s += __hiloint2double((int)(rec.y ^ ((uint32_t)(__popc(rec.z & t0)) << 31)), (int)rec.x);
-            }
-            switch (ent >> 12) {
-              PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
-              PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
-              PSUM_CLASS_CASE(8) PSUM_CLASS_CASE(9) PSUM_CLASS_CASE(10) PSUM_CLASS_CASE(11)
-              PSUM_CLASS_CASE(12) PSUM_CLASS_CASE(13) PSUM_CLASS_CASE(14) PSUM_CLASS_CASE(15)
-            }
-          }
           double2 pv[8];
           if (!remote) {
             const uint32_t tp = t0 ^ xt;
@@ -214,17 +221,51 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
               pv[r] = __ldg(&src[ip ^ ((r & 1) ? b5 : 0ull) ^ ((r & 2) ? b6 : 0ull) ^
                                  ((r & 4) ? b7 : 0ull)]);
           }
-          if (has_im) {
+          const uint2 h1 = reinterpret_cast<const uint2*>(grp)[4 * g + 2];
+          if ((h0.y >> 21) & 1u) {
+            // flat group: one real class-0 entry -> the same D for the 8 amplitudes
+            const double s = pattern_sum(pat4, p, (int)(h1.x & 0xfffu), t0);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              yacc[r].x += D[r] * pv[r].x - D[8 + r] * pv[r].y;
-              yacc[r].y += D[r] * pv[r].y + D[8 + r] * pv[r].x;
+              yacc[r].x = fma(s, pv[r].x, yacc[r].x);
+              yacc[r].y = fma(s, pv[r].y, yacc[r].y);
+            }
+            continue;
+          }
+          const int nent = (int)((h0.y >> 16) & 7u);
+          uint64_t ents = (uint64_t)h1.x | ((uint64_t)h1.y << 32);
+          double D[IM ? 16 : 8];
+#pragma unroll
+          for (int r = 0; r < (IM ? 16 : 8); ++r) D[r] = 0.0;
+          for (int e = 0; e < nent; ++e) {
+            const uint32_t ent = (uint32_t)ents & 0xffffu;
+            ents >>= 16;
+            const double s = pattern_sum(pat4, p, (int)(ent & 0xfffu), t0);
+            if (IM) {
+              switch (ent >> 12) {
+                PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
+                PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
+                PSUM_CLASS_CASE(8) PSUM_CLASS_CASE(9) PSUM_CLASS_CASE(10) PSUM_CLASS_CASE(11)
+                PSUM_CLASS_CASE(12) PSUM_CLASS_CASE(13) PSUM_CLASS_CASE(14) PSUM_CLASS_CASE(15)
+              }
+            } else {
+              switch (ent >> 12) {
+                PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
+                PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
+              }
+            }
+          }
+          if (IM && ((h0.y >> 20) & 1u)) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              yacc[r].x = fma(D[r], pv[r].x, fma(-D[(IM ? 8 : 0) + r], pv[r].y, yacc[r].x));
+              yacc[r].y = fma(D[r], pv[r].y, fma(D[(IM ? 8 : 0) + r], pv[r].x, yacc[r].y));
             }
           } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              yacc[r].x += D[r] * pv[r].x;
-              yacc[r].y += D[r] * pv[r].y;
+              yacc[r].x = fma(D[r], pv[r].x, yacc[r].x);
+              yacc[r].y = fma(D[r], pv[r].y, yacc[r].y);
             }
           }
         }
@@ -238,15 +279,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           eacc.x += b.x * yacc[r].x + b.y * yacc[r].y;
           eacc.y += b.x * yacc[r].y - b.y * yacc[r].x;
         }
-        if (STORE) {
-          double2 o = yacc[r];
-          if (P.accumulate) {
-            const double2 old = y[ir];
-            o.x += old.x;
-            o.y += old.y;
-          }
-          y[ir] = o;
-        }
+        if (STORE) y[ir] = yacc[r];
       }
     }
   }
@@ -282,19 +315,17 @@ k_stream(const double2* __restrict__ src, const double2* __restrict__ bra, doubl
       acc.x += dre * p.x - dim * p.y;
       acc.y += dre * p.y + dim * p.x;
     }
+    if (y && accumulate) {  // the expectation below is then <bra|y> of the final y
+      const double2 old = y[i];
+      acc.x += old.x;
+      acc.y += old.y;
+    }
     if (partial) {
       const double2 b = bra[i];
       eacc.x += b.x * acc.x + b.y * acc.y;
       eacc.y += b.x * acc.y - b.y * acc.x;
     }
-    if (y) {
-      if (accumulate) {
-        const double2 old = y[i];
-        acc.x += old.x;
-        acc.y += old.y;
-      }
-      y[i] = acc;
-    }
+    if (y) y[i] = acc;
   }
   if (partial) {
     double2 tot = block_reduce(eacc, red);

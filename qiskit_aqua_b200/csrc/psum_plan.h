@@ -43,7 +43,7 @@ struct CompTerm {  // real-valued component term of one shard/part: value * (im 
 struct GroupRec {     // 32 bytes
   uint32_t xt;        // tile-local xor (compressed free-set bits of x); bit31 = remote flag
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
-                      // bit 20 = has imaginary patterns
+                      // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry)
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
   uint16_t ent[4];    // non-empty classes: (cls << 12) | count ; cls = im*8 + ((zt >> 5) & 7)
   uint64_t pad;
@@ -68,6 +68,9 @@ constexpr int kGrpChunk = 128;   // groups staged in shared memory at a time
 struct PassHost {
   int L = 0;                   // tile bits
   uint64_t free_mask = 0;      // over local qubits
+  uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..7 register bits, 8.. warp/round
+  bool has_im = false;         // any imaginary component pattern in this pass
+  int64_t n_flat = 0;          // groups whose D is the same for the 8 register amplitudes
   std::vector<GroupRec> groups;
   std::vector<uint16_t> pat_zt;
   std::vector<uint32_t> pat_tptr;  // size patterns+1
@@ -220,6 +223,40 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
   P.free_mask = pc.free_mask;
   P.L = popc64(pc.free_mask);
   const uint64_t S = pc.free_mask;
+  // ---- roles of the free bits -------------------------------------------------------------
+  // tile bits 0..2 = the three lowest free qubits (128-byte lines / conflict-free LDS.128),
+  // tile bits 5..7 (register bits) = the free qubits least often touched by a z-mask of this
+  // pass, so that most groups have the same D for all 8 amplitudes of a thread ("flat"),
+  // the rest ascending.
+  {
+    std::vector<int> fb;
+    for (int b = 0; b < n_loc; ++b)
+      if (S >> b & 1ull) fb.push_back(b);
+    const int L = (int)fb.size();
+    std::vector<double> hits(64, 0.0);
+    for (int mi : pc.members)
+      for (int t : terms_of_mask[mi])
+        for (uint64_t m = comp[t].zl & S; m; m &= m - 1) hits[__builtin_ctzll(m)] += 1.0;
+    std::vector<int> cand(fb.begin() + std::min(3, L), fb.end());
+    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return hits[a] < hits[b]; });
+    std::vector<int> reg(cand.begin(), cand.begin() + std::min<size_t>(3, cand.size()));
+    std::sort(reg.begin(), reg.end());
+    std::vector<int> rest;
+    for (int b : cand)
+      if (std::find(reg.begin(), reg.end(), b) == reg.end()) rest.push_back(b);
+    std::sort(rest.begin(), rest.end());
+    int j = 0;
+    for (int i = 0; i < std::min(3, L); ++i) P.fbit[j++] = (uint8_t)fb[i];
+    size_t ri = 0;
+    while (j < 5 && ri < rest.size()) P.fbit[j++] = (uint8_t)rest[ri++];
+    for (int b : reg) P.fbit[j++] = (uint8_t)b;
+    while (ri < rest.size()) P.fbit[j++] = (uint8_t)rest[ri++];
+  }
+  auto gather = [&](uint64_t v) {  // qubit mask -> tile-index mask
+    uint32_t out = 0;
+    for (int j = 0; j < P.L; ++j) out |= (uint32_t)((v >> P.fbit[j]) & 1ull) << j;
+    return out;
+  };
   struct Key {
     uint8_t im;
     uint32_t zt;
@@ -242,7 +279,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     std::vector<Key> keys;
     keys.reserve(terms_of_mask[mi].size());
     for (int t : terms_of_mask[mi])
-      keys.push_back({comp[t].im, (uint32_t)pext64(comp[t].zl, S), t});
+      keys.push_back({comp[t].im, gather(comp[t].zl), t});
     auto cls_of = [](const Key& k) { return (int)k.im * 8 + (int)((k.zt >> kRegBitLo) & 7); };
     std::stable_sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
       int ca = cls_of(a), cb = cls_of(b);
@@ -264,7 +301,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     while (p < pats.size()) {
       GroupRec G;
       std::memset(&G, 0, sizeof(G));
-      G.xt = (uint32_t)pext64(xl, S) | (remote ? 0x80000000u : 0u);
+      G.xt = gather(xl) | (remote ? 0x80000000u : 0u);
       G.xl = xl;
       int count = 0, nent = 0;
       bool has_im = false;
@@ -283,7 +320,11 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
         ++q;
       }
       if (cur.ng + 1 > kGrpChunk || cur.np + count > kPatChunk) flush_chunk();
-      G.meta = (uint32_t)cur.np | ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u);
+      const bool flat = (nent == 1) && (G.ent[0] >> 12) == 0;
+      G.meta = (uint32_t)cur.np | ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) |
+               (flat ? (1u << 21) : 0u);
+      if (has_im) P.has_im = true;
+      if (flat) P.n_flat++;
       for (size_t j = p; j < q; ++j) {
         P.pat_zt.push_back((uint16_t)pats[j].zt);
         for (int k = pats[j].k0; k < pats[j].k1; ++k) {
