@@ -1,0 +1,143 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/psum.h declares, the
+host-side packing / planning logic, and the host eigen-solvers.  No compute calls (no GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pauli_oracle as po
+from qiskit_aqua_b200 import PauliSumEngine, PsumError, _lib, workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, 'include', 'psum.h')).read()
+    names = set(re.findall(r'\b(psum_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) >= 24
+    lib = C.CDLL(_lib.LIB_PATH)
+    for nm in sorted(names):
+        assert hasattr(lib, nm), 'libpsum.so lacks %s' % nm
+    assert set(_lib.SIGNATURES) == names          # the ctypes table binds exactly the header
+
+
+def test_no_cpu_fallback_without_device():
+    torch = pytest.importorskip('torch')
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    eng = PauliSumEngine.from_labels(['XX', 'ZI'], [1.0, 0.5])
+    with pytest.raises(PsumError) as ei:
+        eng.expect(np.ones(4, dtype=complex))
+    assert ei.value.code == _lib.ERR_CUDA
+
+
+def test_merge_and_flags():
+    eng = PauliSumEngine.from_labels(['XXI', 'XXI', 'ZZI', 'IYY', 'ZZI'], [0.5, 0.25, 1.0, 1j, -1.0])
+    info = eng.info()
+    assert info['n_terms'] == 2 and info['n_xgroups'] == 2
+    assert info['is_hermitian'] == 0 and info['is_diagonal'] == 0
+    eng = PauliSumEngine.from_labels(['ZZI', 'IIZ'], [1.0, 2.0])
+    assert eng.info()['is_diagonal'] == 1 and eng.info()['is_hermitian'] == 1
+    eng = PauliSumEngine.from_labels(['YI', 'XY'], [1.0, -2.0])      # real coeffs on label Paulis
+    assert eng.info()['is_hermitian'] == 1
+
+
+def test_invalid_arguments():
+    x = np.array([1 << 5], dtype=np.uint64)
+    z = np.zeros(1, dtype=np.uint64)
+    with pytest.raises(PsumError):
+        PauliSumEngine(3, x, z, np.zeros(1, np.uint8), np.ones(1, complex))      # mask above n
+    with pytest.raises(PsumError):
+        PauliSumEngine(0, x[:0], z[:0], np.zeros(0, np.uint8), np.ones(0, complex))
+    eng = PauliSumEngine.from_labels(['XX'], [1.0])
+    with pytest.raises(PsumError):
+        eng.set_option('tile_bits', 99)
+    with pytest.raises(PsumError):
+        eng.set_option('no_such_option', 1)
+    with pytest.raises(PsumError):
+        eng.shard(0, 3)                                                         # not a power of 2
+
+
+@pytest.mark.parametrize('tile_bits', [11, 12, 13])
+def test_plan_covers_every_group_once(tile_bits):
+    n, x, z, y, c = W.ising_heisenberg(20, n_triples=600, seed=5)
+    eng = PauliSumEngine(n, x, z, y, c, {'tile_bits': tile_bits})
+    info = eng.info()
+    assert info['tile_bits'] == tile_bits
+    tot = rem = 0
+    for p in range(info['n_passes']):
+        pi = eng.pass_info(p)
+        assert bin(pi['free_mask']).count('1') == tile_bits
+        assert pi['free_mask'] & 0xF == 0xF                       # low bits always free (coalescing)
+        tot += pi['n_groups']
+        rem += pi['n_remote_groups']
+    assert tot == info['n_xgroups'] == len(set(x.tolist()))
+    assert rem == info['n_remote_groups']
+    assert info['n_patterns'] <= info['n_component_terms']
+    assert info['n_passes'] < info['n_xgroups'] / 4               # tiling pays: few HBM sweeps
+
+
+def test_small_operator_uses_streaming_plan():
+    n, x, z, y, c = W.two_local_random(8, 40, seed=1)
+    assert PauliSumEngine(n, x, z, y, c).info()['n_passes'] == 0
+
+
+def test_shard_terms_algebra_world4():
+    """Sum over ranks/parts of the sharded terms reproduces H.psi (pure host logic)."""
+    n, world = 9, 4
+    _, x, z, y, c = W.random_dense_paulis(n, 120, seed=4, complex_coeffs=True)
+    rng = np.random.default_rng(0)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    ref = po.mf_apply(n, x, z, y, c, psi)
+    n_loc = n - 2
+    N_loc = 1 << n_loc
+    out = np.zeros_like(ref)
+    for rank in range(world):
+        eng = PauliSumEngine(n, x, z, y, c)
+        eng.shard(rank, world)
+        assert eng.info()['n_local_qubits'] == n_loc
+        for g in range(world):
+            xl, zl, cl = eng.shard_terms(g)
+            if len(xl) == 0:
+                continue
+            src = psi[((rank ^ g) * N_loc):((rank ^ g) * N_loc + N_loc)]
+            out[rank * N_loc:(rank + 1) * N_loc] += po.mf_apply(
+                n_loc, xl, zl, np.zeros(len(xl), np.uint8), cl, src)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+
+
+def test_host_eigensolvers():
+    lib = _lib.lib()
+    rng = np.random.default_rng(3)
+    dp = C.POINTER(C.c_double)
+    for n in (1, 2, 7, 40):
+        A = rng.standard_normal((n, n))
+        A = A + A.T
+        w = np.zeros(n)
+        V = np.zeros((n, n))
+        assert lib.psum_test_eigh(0, n, A.ctypes.data_as(dp), w.ctypes.data_as(dp), V.ctypes.data_as(dp)) == 0
+        np.testing.assert_allclose(w, np.linalg.eigvalsh(A), atol=1e-12 * max(1, np.abs(A).max() * n))
+        np.testing.assert_allclose(A @ V, V * w, atol=1e-11 * n)
+        d, e = rng.standard_normal(n), rng.standard_normal(n)
+        T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+        de = np.concatenate([d, e])
+        assert lib.psum_test_eigh(1, n, de.ctypes.data_as(dp), w.ctypes.data_as(dp), V.ctypes.data_as(dp)) == 0
+        np.testing.assert_allclose(w, np.linalg.eigvalsh(T), atol=1e-12 * n)
+        np.testing.assert_allclose(T @ V, V * w, atol=1e-11 * n)
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import c_oracle as co
+    n, x, z, y, c = W.random_dense_paulis(13, 80, seed=11, complex_coeffs=True)
+    rng = np.random.default_rng(2)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    ref = po.mf_apply(n, x, z, y, c, psi)
+    np.testing.assert_allclose(co.apply(n, x, z, y, c, psi), ref, atol=1e-12 * np.abs(ref).max())
+    np.testing.assert_allclose(co.apply(n, x, z, y, c, psi, 3, 4099), ref[3:4099], atol=1e-12 * np.abs(ref).max())
+    assert abs(co.expect(n, x, z, y, c, psi) - np.vdot(psi, ref)) < 1e-9
+    s = co.counter_state(5, 0, 1 << n)
+    rows = np.array([0, 17, (1 << n) - 1], dtype=np.uint64)
+    np.testing.assert_allclose(co.apply_rows_counter(x, z, y, c, 5, 1.0, rows),
+                               po.mf_apply(n, x, z, y, c, s, rows), atol=1e-12 * np.abs(ref).max())
