@@ -154,7 +154,7 @@ static int plan(psum_handle_s* h) {
 }
 
 static size_t pass_smem_bytes(int L) {
-  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * kGrpChunk +
+  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * (kGrpChunk + 1) +
          16 * (kThreads / 32);
 }
 
@@ -207,6 +207,7 @@ static int upload(psum_handle_s* h) {
         memset(&dp.params, 0, sizeof(dp.params));
         dp.params.groups = arena_put(base, off, ph.groups, host);
         dp.params.pat_zt = arena_put(base, off, ph.pat_zt, host);
+        dp.params.pat_inl = arena_put(base, off, ph.pat_inl, host);
         dp.params.pat_tptr = arena_put(base, off, ph.pat_tptr, host);
         dp.params.term_zb = arena_put(base, off, ph.term_zb, host);
         dp.params.term_val = arena_put(base, off, ph.term_val, host);
@@ -342,6 +343,7 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
       v[4] += ps.n_remote;
       v[8] += (int64_t)ps.pat_zt.size();
       v[12] += ps.n_flat;
+      v[14] += ps.n_kind_a;
       v[13] += (int64_t)ps.groups.size();
       v[10] = ps.L;
     }

@@ -30,6 +30,7 @@ constexpr int kRoundAmps = kThreads * kAmpsPerThread;  // 2048
 struct PassParams {
   const GroupRec* groups;
   const uint16_t* pat_zt;
+  const uint16_t* pat_inl;
   const uint32_t* pat_tptr;
   const uint64_t* term_zb;
   const double* term_val;
@@ -131,8 +132,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   PatRec* pat = reinterpret_cast<PatRec*>(tile + tile_amps);
   uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
-  GroupRec* grp = reinterpret_cast<GroupRec*>(offHi + 32);
-  double2* red = reinterpret_cast<double2*>(grp + kGrpChunk);
+  uint4* grp4 = reinterpret_cast<uint4*>(offHi + 32);               // 3 x uint4 per group record
+  double2* red = reinterpret_cast<double2*>(grp4 + 3 * (kGrpChunk + 1));
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -155,9 +156,15 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 
   double2 eacc = make_double2(0.0, 0.0);
 
-  // fold: bits outside the free set become a per-tile sign of each term; equal in-tile patterns
-  // of a group are summed into one coefficient.  Also stages the chunk's group records.
+  // Stage a chunk: copy its group records to shared memory, then fold -- bits outside the free
+  // set become a per-tile sign of each term; equal in-tile patterns of a group are summed into
+  // one coefficient, stored in pat[] and (first two patterns of a group) inline in its record.
   auto stage_chunk = [&](const ChunkRec ch, uint64_t base) {
+    const int ng = ch.ng & 0xffff;
+    for (int g = tid; g < ng * 3; g += kThreads)
+      grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
+    if (tid < 3) grp4[ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);  // prefetch overrun record
+    __syncthreads();
     for (int p = tid; p < ch.np; p += kThreads) {
       const int gp = ch.p0 + p;
       const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
@@ -170,9 +177,10 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       rec.z = P.pat_zt[gp];
       rec.w = 0;
       reinterpret_cast<uint4*>(pat)[p] = rec;
+      const uint32_t inl = P.pat_inl[gp];
+      if (inl != 0xffffu)
+        reinterpret_cast<double*>(grp4 + 3 * (inl >> 1) + 1)[inl & 1u] = v;
     }
-    for (int g = tid; g < ch.ng * 2; g += kThreads)
-      reinterpret_cast<uint4*>(grp)[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
   };
 
   for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
@@ -203,9 +211,34 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           stage_chunk(ch, base);
           __syncthreads();
         }
+        const int ng = ch.ng & 0xffff, ng_a = ch.ng >> 16;
 
-        for (int g = 0; g < ch.ng; ++g) {
-          const uint4 h0 = reinterpret_cast<const uint4*>(grp)[2 * g];
+        // ---- loop A: local, flat, real groups with <= 2 patterns (branch-free) --------------
+        {
+          uint4 h0 = grp4[0], hc = grp4[1];
+          for (int g = 0; g < ng_a; ++g) {
+            const uint4 n0 = grp4[3 * g + 3], nc = grp4[3 * g + 4];  // next record (or the dummy)
+            const uint32_t tp = t0 ^ h0.x;
+            double2 pv[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
+            const double s =
+                __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x) +
+                __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              yacc[r].x = fma(s, pv[r].x, yacc[r].x);
+              yacc[r].y = fma(s, pv[r].y, yacc[r].y);
+            }
+            h0 = n0;
+            hc = nc;
+          }
+        }
+
+        // ---- loop B: everything else ------------------------------------------------------------
+        for (int g = ng_a; g < ng; ++g) {
+          const uint4 h0 = grp4[3 * g];
+          const uint4 h2 = grp4[3 * g + 2];
           const uint32_t xt = h0.x & 0x7fffffffu;
           const bool remote = (h0.x >> 31) != 0;
           int p = (int)(h0.y & 0xffffu);
@@ -215,16 +248,15 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
             for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
           } else {
-            const uint64_t ip = i0 ^ ((uint64_t)h0.z | ((uint64_t)h0.w << 32));
+            const uint64_t ip = i0 ^ ((uint64_t)h2.x | ((uint64_t)h2.y << 32));
 #pragma unroll
             for (int r = 0; r < 8; ++r)
               pv[r] = __ldg(&src[ip ^ ((r & 1) ? b5 : 0ull) ^ ((r & 2) ? b6 : 0ull) ^
                                  ((r & 4) ? b7 : 0ull)]);
           }
-          const uint2 h1 = reinterpret_cast<const uint2*>(grp)[4 * g + 2];
           if ((h0.y >> 21) & 1u) {
             // flat group: one real class-0 entry -> the same D for the 8 amplitudes
-            const double s = pattern_sum(pat4, p, (int)(h1.x & 0xfffu), t0);
+            const double s = pattern_sum(pat4, p, (int)(h2.z & 0xfffu), t0);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
               yacc[r].x = fma(s, pv[r].x, yacc[r].x);
@@ -233,7 +265,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
             continue;
           }
           const int nent = (int)((h0.y >> 16) & 7u);
-          uint64_t ents = (uint64_t)h1.x | ((uint64_t)h1.y << 32);
+          uint64_t ents = (uint64_t)h2.z | ((uint64_t)h2.w << 32);
           double D[IM ? 16 : 8];
 #pragma unroll
           for (int r = 0; r < (IM ? 16 : 8); ++r) D[r] = 0.0;

@@ -40,15 +40,16 @@ struct CompTerm {  // real-valued component term of one shard/part: value * (im 
 };
 
 // ---- device-facing records (layout shared with the kernels) --------------------------------
-struct GroupRec {     // 32 bytes
-  uint32_t xt;        // tile-local xor (compressed free-set bits of x); bit31 = remote flag
+struct GroupRec {     // 48 bytes
+  uint32_t xt;        // tile-local xor (x gathered onto the tile index); bit31 = remote flag
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
                       // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry)
+  uint32_t zt0, zt1;  // in-tile z-patterns of the first two patterns (inline copy)
+  double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
   uint16_t ent[4];    // non-empty classes: (cls << 12) | count ; cls = im*8 + ((zt >> 5) & 7)
-  uint64_t pad;
 };
-static_assert(sizeof(GroupRec) == 32, "GroupRec layout");
+static_assert(sizeof(GroupRec) == 48, "GroupRec layout");
 
 struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is written by the fold)
   double cf;
@@ -57,7 +58,10 @@ struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is writ
 };
 
 struct ChunkRec {  // 16 bytes
-  int32_t g0, ng, p0, np;
+  int32_t g0;  // first group
+  int32_t ng;  // low 16 bits: groups in the chunk; high 16 bits: how many of them (the first
+               // ones) are "kind A": local, flat, real, <= 2 patterns -> branch-free fast loop
+  int32_t p0, np;
 };
 
 constexpr int kMaxTileBits = 13;
@@ -71,8 +75,10 @@ struct PassHost {
   uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..7 register bits, 8.. warp/round
   bool has_im = false;         // any imaginary component pattern in this pass
   int64_t n_flat = 0;          // groups whose D is the same for the 8 register amplitudes
+  int64_t n_kind_a = 0;        // of those: local, <= 2 patterns (fast loop)
   std::vector<GroupRec> groups;
   std::vector<uint16_t> pat_zt;
+  std::vector<uint16_t> pat_inl;   // (group index in chunk) * 2 + slot for inlined patterns, else 0xffff
   std::vector<uint32_t> pat_tptr;  // size patterns+1
   std::vector<uint64_t> term_zb;
   std::vector<double> term_val;
@@ -262,15 +268,9 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     uint32_t zt;
     int term;
   };
-  ChunkRec cur{0, 0, 0, 0};
-  auto flush_chunk = [&]() {
-    if (cur.ng > 0) P.chunks.push_back(cur);
-    cur.g0 += cur.ng;
-    cur.p0 += cur.np;
-    cur.ng = 0;
-    cur.np = 0;
-  };
-  P.pat_tptr.push_back(0);
+  struct PatTmp { int cls; uint32_t zt; std::vector<int> terms; };
+  struct SubGroup { GroupRec G; std::vector<PatTmp> pats; bool kind_a; };
+  std::vector<SubGroup> subs;
   for (int mi : pc.members) {
     const uint64_t xl = masks[mi];
     const bool remote = (xl & ~S) != 0;
@@ -287,19 +287,21 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       return a.zt < b.zt;
     });
     // patterns = runs of equal (im, zt)
-    struct Pat { int cls; uint32_t zt; int k0, k1; };
-    std::vector<Pat> pats;
+    std::vector<PatTmp> pats;
     for (int k = 0; k < (int)keys.size();) {
       int e = k;
-      while (e < (int)keys.size() && keys[e].im == keys[k].im && keys[e].zt == keys[k].zt) ++e;
-      pats.push_back({cls_of(keys[k]), keys[k].zt, k, e});
+      PatTmp pt{cls_of(keys[k]), keys[k].zt, {}};
+      while (e < (int)keys.size() && keys[e].im == keys[k].im && keys[e].zt == keys[k].zt)
+        pt.terms.push_back(keys[e++].term);
+      pats.push_back(std::move(pt));
       k = e;
     }
-    // emit sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 4095
-    // patterns per class.  Patterns are in class order, so cut greedily.
+    // sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 4095 patterns
+    // per class.  Patterns are in class order, so cut greedily.
     size_t p = 0;
     while (p < pats.size()) {
-      GroupRec G;
+      SubGroup sg;
+      GroupRec& G = sg.G;
       std::memset(&G, 0, sizeof(G));
       G.xt = gather(xl) | (remote ? 0x80000000u : 0u);
       G.xl = xl;
@@ -319,28 +321,53 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
         ++count;
         ++q;
       }
-      if (cur.ng + 1 > kGrpChunk || cur.np + count > kPatChunk) flush_chunk();
       const bool flat = (nent == 1) && (G.ent[0] >> 12) == 0;
-      G.meta = (uint32_t)cur.np | ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) |
-               (flat ? (1u << 21) : 0u);
+      G.meta = ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) | (flat ? (1u << 21) : 0u);
+      G.zt0 = pats[p].zt;
+      G.zt1 = count > 1 ? pats[p + 1].zt : 0u;
+      sg.kind_a = flat && !remote && count <= 2;
       if (has_im) P.has_im = true;
       if (flat) P.n_flat++;
-      for (size_t j = p; j < q; ++j) {
-        P.pat_zt.push_back((uint16_t)pats[j].zt);
-        for (int k = pats[j].k0; k < pats[j].k1; ++k) {
-          const CompTerm& ct = comp[keys[k].term];
-          P.term_zb.push_back(ct.zl & ~S);
-          P.term_val.push_back(ct.val);
-        }
-        P.pat_tptr.push_back((uint32_t)P.term_val.size());
-      }
-      P.groups.push_back(G);
-      cur.ng++;
-      cur.np += count;
+      if (sg.kind_a) P.n_kind_a++;
+      sg.pats.assign(pats.begin() + p, pats.begin() + q);
+      subs.push_back(std::move(sg));
       p = q;
     }
   }
-  flush_chunk();
+  // chunks: consecutive sub-groups up to the staging capacity; inside a chunk kind A goes first
+  P.pat_tptr.push_back(0);
+  size_t s0 = 0;
+  int g0 = 0, p0 = 0;
+  while (s0 < subs.size()) {
+    size_t s1 = s0;
+    int np = 0;
+    while (s1 < subs.size() && (int)(s1 - s0) < kGrpChunk && np + (int)subs[s1].pats.size() <= kPatChunk) {
+      np += (int)subs[s1].pats.size();
+      ++s1;
+    }
+    std::stable_partition(subs.begin() + s0, subs.begin() + s1, [](const SubGroup& a) { return a.kind_a; });
+    int ng_a = 0, pl = 0;
+    for (size_t si = s0; si < s1; ++si) {
+      SubGroup& sg = subs[si];
+      if (sg.kind_a) ++ng_a;
+      sg.G.meta |= (uint32_t)pl;
+      for (size_t j = 0; j < sg.pats.size(); ++j) {
+        P.pat_zt.push_back((uint16_t)sg.pats[j].zt);
+        P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + j) : (uint16_t)0xffff);
+        for (int t : sg.pats[j].terms) {
+          P.term_zb.push_back(comp[t].zl & ~S);
+          P.term_val.push_back(comp[t].val);
+        }
+        P.pat_tptr.push_back((uint32_t)P.term_val.size());
+        ++pl;
+      }
+      P.groups.push_back(sg.G);
+    }
+    P.chunks.push_back({g0, (int32_t)((s1 - s0) | ((size_t)ng_a << 16)), p0, np});
+    g0 += (int)(s1 - s0);
+    p0 += np;
+    s0 = s1;
+  }
   (void)n_loc;
   return P;
 }
