@@ -104,6 +104,16 @@ __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
     }                                                            \
   } break;
 
+// yacc[r] += (s0 + (-1)^{popc(r & C)} s1) * pv[r]  with C the compile-time class of slot 1
+#define PSUM_PAIR_CASE(C)                                        \
+  case C: {                                                      \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) {              \
+      const double d = (__popc(r & (C)) & 1) ? dm : dp;          \
+      yacc[r].x = fma(d, pv[r].x, yacc[r].x);                    \
+      yacc[r].y = fma(d, pv[r].y, yacc[r].y);                    \
+    }                                                            \
+  } break;
+
 // sum of the (tile-folded, thread-signed) coefficients of `cnt` patterns starting at p
 __device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, int& p, int cnt, uint32_t t0) {
   double s = 0.0;
@@ -213,7 +223,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         }
         const int ng = ch.ng & 0xffff, ng_a = ch.ng >> 16;
 
-        // ---- loop A: local, flat, real groups with <= 2 patterns (branch-free) --------------
+        // ---- loop A: local real groups with <= 2 patterns (slot 0 class 0, slot 1 class c1) ----
         {
           uint4 h0 = grp4[0], hc = grp4[1];
           for (int g = 0; g < ng_a; ++g) {
@@ -222,13 +232,12 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
             double2 pv[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
-            const double s =
-                __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x) +
-                __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              yacc[r].x = fma(s, pv[r].x, yacc[r].x);
-              yacc[r].y = fma(s, pv[r].y, yacc[r].y);
+            const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
+            const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+            const double dp = s0 + s1, dm = s0 - s1;
+            switch ((h0.y >> 24) & 7u) {
+              PSUM_PAIR_CASE(0) PSUM_PAIR_CASE(1) PSUM_PAIR_CASE(2) PSUM_PAIR_CASE(3)
+              PSUM_PAIR_CASE(4) PSUM_PAIR_CASE(5) PSUM_PAIR_CASE(6) PSUM_PAIR_CASE(7)
             }
             h0 = n0;
             hc = nc;
@@ -321,6 +330,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   }
 }
 #undef PSUM_CLASS_CASE
+#undef PSUM_PAIR_CASE
 
 // ------------------------------------------------------------------------------------------
 // Kernel A: streaming form, one amplitude per thread (grid-stride).  Any n_loc >= 0.

@@ -43,7 +43,8 @@ struct CompTerm {  // real-valued component term of one shard/part: value * (im 
 struct GroupRec {     // 48 bytes
   uint32_t xt;        // tile-local xor (x gathered onto the tile index); bit31 = remote flag
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
-                      // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry)
+                      // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry),
+                      // bits 24..26 = class of the inline pattern in slot 1 (kind A groups)
   uint32_t zt0, zt1;  // in-tile z-patterns of the first two patterns (inline copy)
   double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
@@ -60,7 +61,7 @@ struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is writ
 struct ChunkRec {  // 16 bytes
   int32_t g0;  // first group
   int32_t ng;  // low 16 bits: groups in the chunk; high 16 bits: how many of them (the first
-               // ones) are "kind A": local, flat, real, <= 2 patterns -> branch-free fast loop
+               // ones) are "kind A": local, real, <= 2 patterns with slot 0 of class 0 -> fast loop
   int32_t p0, np;
 };
 
@@ -269,7 +270,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     int term;
   };
   struct PatTmp { int cls; uint32_t zt; std::vector<int> terms; };
-  struct SubGroup { GroupRec G; std::vector<PatTmp> pats; bool kind_a; };
+  struct SubGroup { GroupRec G; std::vector<PatTmp> pats; bool kind_a; int slot_of[2]; };
   std::vector<SubGroup> subs;
   for (int mi : pc.members) {
     const uint64_t xl = masks[mi];
@@ -323,9 +324,24 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       }
       const bool flat = (nent == 1) && (G.ent[0] >> 12) == 0;
       G.meta = ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) | (flat ? (1u << 21) : 0u);
-      G.zt0 = pats[p].zt;
-      G.zt1 = count > 1 ? pats[p + 1].zt : 0u;
-      sg.kind_a = flat && !remote && count <= 2;
+      // kind A: local, real, at most two patterns, the first (if two) of class 0.  Slot 0 of the
+      // inline copy holds the class-0 pattern (or nothing), slot 1 the other one with its class.
+      sg.kind_a = !remote && !has_im && count <= 2 && (count == 1 || pats[p].cls == 0);
+      sg.slot_of[0] = 0;
+      sg.slot_of[1] = 1;
+      if (sg.kind_a) {
+        if (count == 1 && pats[p].cls != 0) sg.slot_of[0] = 1;   // lone non-flat pattern -> slot 1
+        for (int j = 0; j < count; ++j) {
+          if (sg.slot_of[j] == 0) G.zt0 = pats[p + j].zt;
+          else {
+            G.zt1 = pats[p + j].zt;
+            G.meta |= (uint32_t)(pats[p + j].cls & 7) << 24;
+          }
+        }
+      } else {
+        G.zt0 = pats[p].zt;
+        G.zt1 = count > 1 ? pats[p + 1].zt : 0u;
+      }
       if (has_im) P.has_im = true;
       if (flat) P.n_flat++;
       if (sg.kind_a) P.n_kind_a++;
@@ -353,7 +369,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       sg.G.meta |= (uint32_t)pl;
       for (size_t j = 0; j < sg.pats.size(); ++j) {
         P.pat_zt.push_back((uint16_t)sg.pats[j].zt);
-        P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + j) : (uint16_t)0xffff);
+        P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
         for (int t : sg.pats[j].terms) {
           P.term_zb.push_back(comp[t].zl & ~S);
           P.term_val.push_back(comp[t].val);
