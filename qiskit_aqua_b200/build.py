@@ -24,6 +24,7 @@ def build_lib(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     cmd = [nvcc, '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
            '-Xcompiler', '-fPIC', '-shared', '-o', LIB]
+    cmd += os.environ.get('PSUM_NVCC_FLAGS', '').split()
     if verbose:
         cmd += ['-Xptxas', '-v']
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']

@@ -132,8 +132,11 @@ __device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, in
 //   IM    : the pass has imaginary component patterns (complex D); real-only passes carry half
 //           the class accumulators
 //   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
+#ifndef PSUM_MIN_CTAS
+#define PSUM_MIN_CTAS 2
+#endif
 template <bool STORE, bool EXPECT, bool IM>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, IM ? 2 : PSUM_MIN_CTAS)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
        const PassParams P, double2* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

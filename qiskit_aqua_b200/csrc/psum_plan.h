@@ -67,8 +67,14 @@ struct ChunkRec {  // 16 bytes
 
 constexpr int kMaxTileBits = 13;
 constexpr int kRegBitLo = 5;     // tile bits 5..7 live in registers (8 amplitudes per thread)
-constexpr int kPatChunk = 1024;  // patterns staged in shared memory at a time
-constexpr int kGrpChunk = 128;   // groups staged in shared memory at a time
+#ifndef PSUM_PAT_CHUNK
+#define PSUM_PAT_CHUNK 1024
+#endif
+#ifndef PSUM_GRP_CHUNK
+#define PSUM_GRP_CHUNK 128
+#endif
+constexpr int kPatChunk = PSUM_PAT_CHUNK;  // patterns staged in shared memory at a time
+constexpr int kGrpChunk = PSUM_GRP_CHUNK;  // groups staged in shared memory at a time
 
 struct PassHost {
   int L = 0;                   // tile bits
