@@ -155,7 +155,7 @@ static int plan(psum_handle_s* h) {
 
 static size_t pass_smem_bytes(int L) {
   return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * (kGrpChunk + 1) +
-         16 * (kThreads / 32);
+         16 * (kThreads / 32) + 8 * 9 * 64;
 }
 
 template <typename T>
@@ -220,6 +220,12 @@ static int upload(psum_handle_s* h) {
         for (int b = 0; b < h->n_loc; ++b)
           if (!(ph.free_mask >> b & 1ull)) dp.params.nbit[nj++] = (uint8_t)b;
         for (int j = 0; j < ph.L; ++j) dp.params.fbit[j] = ph.fbit[j];
+        for (int r = 0; r < 8; ++r) {
+          uint64_t o = 0;
+          for (int b = 0; b < 3; ++b)
+            if (r >> b & 1) o |= 1ull << ph.fbit[5 + b];
+          dp.params.roff[r] = 16ull * o;
+        }
         dp.has_im = ph.has_im;
         dp.smem = pass_smem_bytes(ph.L);
         int per_sm = dp.smem > 113 * 1024 ? 1 : 2;

@@ -40,7 +40,8 @@ struct PassParams {
   int n_nonfree;
   int accumulate;
   uint64_t ntiles;
-  uint8_t fbit[16];  // positions of the free bits, ascending
+  uint64_t roff[8];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
+  uint8_t fbit[16];  // qubit of tile bit j (0..4 lane, 5..7 register, 8.. warp/round)
   uint8_t nbit[64];  // positions of the non-free local bits, ascending
 };
 
@@ -147,6 +148,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
   uint4* grp4 = reinterpret_cast<uint4*>(offHi + 32);               // 3 x uint4 per group record
   double2* red = reinterpret_cast<double2*>(grp4 + 3 * (kGrpChunk + 1));
+  uint64_t* baseT = reinterpret_cast<uint64_t*>(red + kThreads / 32);  // [9][64] deposit tables
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -162,6 +164,15 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     for (int j = 8; j < L; ++j) o |= (uint64_t)((tid >> (j - 8)) & 1) << P.fbit[j];
     offHi[tid] = o;
   }
+  // tile id -> base index: 6 bits of the tile id per table lookup
+  const int nbt = (P.n_nonfree + 5) / 6;
+  for (int e = tid; e < nbt * 64; e += kThreads) {
+    const int k = e >> 6, v = e & 63;
+    uint64_t o = 0;
+    for (int j = 0; j < 6 && 6 * k + j < P.n_nonfree; ++j) o |= (uint64_t)((v >> j) & 1) << P.nbit[6 * k + j];
+    baseT[e] = o;
+  }
+  __syncthreads();
   const uint64_t b5 = 1ull << P.fbit[5], b6 = 1ull << P.fbit[6], b7 = 1ull << P.fbit[7];
   const int nrounds = (int)(tile_amps / kRoundAmps);
   const int nload = (int)(tile_amps / kThreads);
@@ -198,9 +209,9 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 
   for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
     uint64_t base = 0;
-    for (int j = 0; j < P.n_nonfree; ++j) base |= ((tile_id >> j) & 1ull) << P.nbit[j];
+    for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
 
-    __syncthreads();  // previous tile fully consumed; offHi visible on the first trip
+    __syncthreads();  // previous tile fully consumed
     for (int j = 0; j < nload; ++j)
       cp_async16(&tile[j * kThreads + tid], &src[base | offLo8 | offHi[j]]);
     if (one_chunk) stage_chunk(P.chunks[0], base);  // overlaps the tile load
@@ -211,11 +222,11 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       const uint32_t t0 = (uint32_t)rnd * kRoundAmps + (uint32_t)warp * 256u + (uint32_t)lane;
       const uint64_t i0 = base | offLane | offHi[rnd * 8 + warp];
       double2 yacc[8];
+      const char* ybase = reinterpret_cast<const char*>(y + i0);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint64_t ir = i0 | ((r & 1) ? b5 : 0ull) | ((r & 2) ? b6 : 0ull) | ((r & 4) ? b7 : 0ull);
-        yacc[r] = (STORE && P.accumulate) ? y[ir] : make_double2(0.0, 0.0);
-      }
+      for (int r = 0; r < 8; ++r)
+        yacc[r] = (STORE && P.accumulate) ? *reinterpret_cast<const double2*>(ybase + P.roff[r])
+                                          : make_double2(0.0, 0.0);
 
       for (int c = 0; c < P.nchunks; ++c) {
         const ChunkRec ch = P.chunks[c];
@@ -226,24 +237,40 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         }
         const int ng = ch.ng & 0xffff, ng_a = ch.ng >> 16;
 
-        // ---- loop A: local real groups with <= 2 patterns (slot 0 class 0, slot 1 class c1) ----
+        // ---- loop A: local real groups with <= 2 patterns (slot 0 class 0, slot 1 class c1), sorted
+        // by c1 so that each class runs its own branch-free loop with compile-time signs ----------
         {
-          uint4 h0 = grp4[0], hc = grp4[1];
-          for (int g = 0; g < ng_a; ++g) {
-            const uint4 n0 = grp4[3 * g + 3], nc = grp4[3 * g + 4];  // next record (or the dummy)
-            const uint32_t tp = t0 ^ h0.x;
-            double2 pv[8];
+          int g = 0;
+          const uint64_t acnt = *reinterpret_cast<const uint64_t*>(ch.a_cnt);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
-            const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
-            const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
-            const double dp = s0 + s1, dm = s0 - s1;
-            switch ((h0.y >> 24) & 7u) {
-              PSUM_PAIR_CASE(0) PSUM_PAIR_CASE(1) PSUM_PAIR_CASE(2) PSUM_PAIR_CASE(3)
-              PSUM_PAIR_CASE(4) PSUM_PAIR_CASE(5) PSUM_PAIR_CASE(6) PSUM_PAIR_CASE(7)
+          for (int cls = 0; cls < 8; ++cls) {
+            const int gend = g + (int)((acnt >> (8 * cls)) & 0xffull);
+            for (; g < gend; ++g) {
+              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+              const uint32_t tp = t0 ^ h0.x;
+              double2 pv[8];
+#pragma unroll
+              for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
+              const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
+              if (cls == 0) {  // flat: slot 1 (if any) is class 0 too
+                const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+                const double d = s0 + s1;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                  yacc[r].x = fma(d, pv[r].x, yacc[r].x);
+                  yacc[r].y = fma(d, pv[r].y, yacc[r].y);
+                }
+              } else {
+                const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+                const double dp = s0 + s1, dm = s0 - s1;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                  const double d = (__popc(r & cls) & 1) ? dm : dp;
+                  yacc[r].x = fma(d, pv[r].x, yacc[r].x);
+                  yacc[r].y = fma(d, pv[r].y, yacc[r].y);
+                }
+              }
             }
-            h0 = n0;
-            hc = nc;
           }
         }
 
@@ -317,13 +344,15 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       // epilogue of the round: y and/or the expectation partial
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const uint64_t ir = i0 | ((r & 1) ? b5 : 0ull) | ((r & 2) ? b6 : 0ull) | ((r & 4) ? b7 : 0ull);
         if (EXPECT) {
-          const double2 b = bra ? __ldg(&bra[ir]) : tile[t0 | ((uint32_t)r << 5)];
+          const double2 b = bra ? __ldg(reinterpret_cast<const double2*>(
+                                      reinterpret_cast<const char*>(bra + i0) + P.roff[r]))
+                                : tile[t0 | ((uint32_t)r << 5)];
           eacc.x += b.x * yacc[r].x + b.y * yacc[r].y;
           eacc.y += b.x * yacc[r].y - b.y * yacc[r].x;
         }
-        if (STORE) y[ir] = yacc[r];
+        if (STORE)
+          *reinterpret_cast<double2*>(reinterpret_cast<char*>(y + i0) + P.roff[r]) = yacc[r];
       }
     }
   }

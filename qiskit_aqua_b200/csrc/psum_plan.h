@@ -58,12 +58,15 @@ struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is writ
   uint32_t pad;
 };
 
-struct ChunkRec {  // 16 bytes
+struct ChunkRec {  // 32 bytes
   int32_t g0;  // first group
   int32_t ng;  // low 16 bits: groups in the chunk; high 16 bits: how many of them (the first
                // ones) are "kind A": local, real, <= 2 patterns with slot 0 of class 0 -> fast loop
   int32_t p0, np;
+  uint8_t a_cnt[8];  // kind A groups are sorted by the class of slot 1: count per class
+  uint64_t pad;
 };
+static_assert(sizeof(ChunkRec) == 32, "ChunkRec layout");
 
 constexpr int kMaxTileBits = 13;
 constexpr int kRegBitLo = 5;     // tile bits 5..7 live in registers (8 amplitudes per thread)
@@ -367,11 +370,19 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       np += (int)subs[s1].pats.size();
       ++s1;
     }
-    std::stable_partition(subs.begin() + s0, subs.begin() + s1, [](const SubGroup& a) { return a.kind_a; });
+    std::stable_sort(subs.begin() + s0, subs.begin() + s1, [](const SubGroup& a, const SubGroup& b) {
+      const int ka = a.kind_a ? (int)((a.G.meta >> 24) & 7u) : 8, kb = b.kind_a ? (int)((b.G.meta >> 24) & 7u) : 8;
+      return ka < kb;
+    });
+    ChunkRec cr;
+    std::memset(&cr, 0, sizeof(cr));
     int ng_a = 0, pl = 0;
     for (size_t si = s0; si < s1; ++si) {
       SubGroup& sg = subs[si];
-      if (sg.kind_a) ++ng_a;
+      if (sg.kind_a) {
+        ++ng_a;
+        cr.a_cnt[(sg.G.meta >> 24) & 7u]++;
+      }
       sg.G.meta |= (uint32_t)pl;
       for (size_t j = 0; j < sg.pats.size(); ++j) {
         P.pat_zt.push_back((uint16_t)sg.pats[j].zt);
@@ -385,7 +396,11 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       }
       P.groups.push_back(sg.G);
     }
-    P.chunks.push_back({g0, (int32_t)((s1 - s0) | ((size_t)ng_a << 16)), p0, np});
+    cr.g0 = g0;
+    cr.ng = (int32_t)((s1 - s0) | ((size_t)ng_a << 16));
+    cr.p0 = p0;
+    cr.np = np;
+    P.chunks.push_back(cr);
     g0 += (int)(s1 - s0);
     p0 += np;
     s0 = s1;

@@ -14,10 +14,12 @@ def launches(path, out, per_step):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr = rows[0]
     ki, mi, vi, ii = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('ID')
+    ui = hdr.index('Metric Unit')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12, 'ns': 1.0, 'us': 1e3, 'ms': 1e6, 's': 1e9}
     per = collections.OrderedDict()
     for r in rows[1:]:
         d = per.setdefault(int(r[ii]), {'kernel': r[ki].split('(')[0]})
-        d[r[mi]] = float(r[vi].replace(',', ''))
+        d[r[mi]] = float(r[vi].replace(',', '')) * scale.get(r[ui], 1.0)
     seq = list(per.values())
     kp = [d for d in seq if 'k_pass' in d['kernel']]
     step = kp[-per_step:]
@@ -37,14 +39,14 @@ def launches(path, out, per_step):
     tb = 0.0
     for i, d in enumerate(step):
         rd, wr, t = d.get('dram__bytes_read.sum', 0.0), d.get('dram__bytes_write.sum', 0.0), d['gpu__time_duration.sum']
-        unit = 1.0
+        unit = 1e-9
         tb += rd + wr
         lines.append('| %d | %.2f | %.2f | %.2f | %.0f |' % (i, t / 1e6, rd * unit, wr * unit, (rd + wr) * unit / (t / 1e9) if t else 0))
     tstep = sum(d['gpu__time_duration.sum'] for d in step) / 1e6
-    lines += ['', 'step total: %.1f ms under ncu, DRAM traffic %.1f GB per step' % (tstep, tb)]
+    lines += ['', 'step total: %.1f ms under ncu, DRAM traffic %.1f GB per step' % (tstep, tb / 1e9)]
     open(out, 'w').write('\n'.join(lines) + '\n')
-    return {'dram_bytes_per_step': tb * 1e9, 'ms_per_step_under_ncu': tstep,
-            'per_launch_dram_bytes': [(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0)) * 1e9 for d in step]}
+    return {'dram_bytes_per_step': tb, 'ms_per_step_under_ncu': tstep,
+            'per_launch_dram_bytes': [d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in step]}
 
 
 WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
