@@ -304,7 +304,7 @@ def main():
     achieved = b_alg / (ms_step * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1 and args.workload == 'c4' and n_loc == 30:
         try:
             traffic = json.load(open(tpath)).get('dram_bytes_per_step')
         except Exception:

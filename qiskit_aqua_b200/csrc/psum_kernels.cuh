@@ -241,10 +241,11 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         // by c1 so that each class runs its own branch-free loop with compile-time signs ----------
         {
           int g = 0;
-          const uint64_t acnt = *reinterpret_cast<const uint64_t*>(ch.a_cnt);
+          const uint64_t acnt_re = reinterpret_cast<const uint64_t*>(ch.a_cnt)[0];
+          const uint64_t acnt_im = reinterpret_cast<const uint64_t*>(ch.a_cnt)[1];
 #pragma unroll
-          for (int cls = 0; cls < 8; ++cls) {
-            const int gend = g + (int)((acnt >> (8 * cls)) & 0xffull);
+          for (int cls = 0; cls < (IM ? 16 : 8); ++cls) {
+            const int gend = g + (int)(((cls < 8 ? acnt_re : acnt_im) >> (8 * (cls & 7))) & 0xffull);
             for (; g < gend; ++g) {
               const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
               const uint32_t tp = t0 ^ h0.x;
@@ -252,22 +253,28 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
               for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
               const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
-              if (cls == 0) {  // flat: slot 1 (if any) is class 0 too
-                const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+              const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+              if (cls == 0) {  // flat: slot 1 (if any) is real class 0 too
                 const double d = s0 + s1;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                   yacc[r].x = fma(d, pv[r].x, yacc[r].x);
                   yacc[r].y = fma(d, pv[r].y, yacc[r].y);
                 }
-              } else {
-                const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
+              } else if (cls < 8) {
                 const double dp = s0 + s1, dm = s0 - s1;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                   const double d = (__popc(r & cls) & 1) ? dm : dp;
                   yacc[r].x = fma(d, pv[r].x, yacc[r].x);
                   yacc[r].y = fma(d, pv[r].y, yacc[r].y);
+                }
+              } else {  // slot 1 is imaginary: D = s0 + i (+-s1)
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                  const double di = (__popc(r & (cls & 7)) & 1) ? -s1 : s1;
+                  yacc[r].x = fma(s0, pv[r].x, fma(-di, pv[r].y, yacc[r].x));
+                  yacc[r].y = fma(s0, pv[r].y, fma(di, pv[r].x, yacc[r].y));
                 }
               }
             }

@@ -44,7 +44,7 @@ struct GroupRec {     // 48 bytes
   uint32_t xt;        // tile-local xor (x gathered onto the tile index); bit31 = remote flag
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
                       // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry),
-                      // bits 24..26 = class of the inline pattern in slot 1 (kind A groups)
+                      // bits 24..27 = class (im*8 + zr) of the inline pattern in slot 1 (kind A groups)
   uint32_t zt0, zt1;  // in-tile z-patterns of the first two patterns (inline copy)
   double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
@@ -63,8 +63,8 @@ struct ChunkRec {  // 32 bytes
   int32_t ng;  // low 16 bits: groups in the chunk; high 16 bits: how many of them (the first
                // ones) are "kind A": local, real, <= 2 patterns with slot 0 of class 0 -> fast loop
   int32_t p0, np;
-  uint8_t a_cnt[8];  // kind A groups are sorted by the class of slot 1: count per class
-  uint64_t pad;
+  uint8_t a_cnt[16];  // kind A groups are sorted by the class of slot 1 (0..7 real, 8..15
+                      // imaginary): count per class
 };
 static_assert(sizeof(ChunkRec) == 32, "ChunkRec layout");
 
@@ -335,7 +335,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       G.meta = ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) | (flat ? (1u << 21) : 0u);
       // kind A: local, real, at most two patterns, the first (if two) of class 0.  Slot 0 of the
       // inline copy holds the class-0 pattern (or nothing), slot 1 the other one with its class.
-      sg.kind_a = !remote && !has_im && count <= 2 && (count == 1 || pats[p].cls == 0);
+      sg.kind_a = !remote && count <= 2 && (count == 1 || pats[p].cls == 0);
       sg.slot_of[0] = 0;
       sg.slot_of[1] = 1;
       if (sg.kind_a) {
@@ -344,7 +344,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
           if (sg.slot_of[j] == 0) G.zt0 = pats[p + j].zt;
           else {
             G.zt1 = pats[p + j].zt;
-            G.meta |= (uint32_t)(pats[p + j].cls & 7) << 24;
+            G.meta |= (uint32_t)(pats[p + j].cls & 15) << 24;
           }
         }
       } else {
@@ -371,7 +371,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       ++s1;
     }
     std::stable_sort(subs.begin() + s0, subs.begin() + s1, [](const SubGroup& a, const SubGroup& b) {
-      const int ka = a.kind_a ? (int)((a.G.meta >> 24) & 7u) : 8, kb = b.kind_a ? (int)((b.G.meta >> 24) & 7u) : 8;
+      const int ka = a.kind_a ? (int)((a.G.meta >> 24) & 15u) : 16, kb = b.kind_a ? (int)((b.G.meta >> 24) & 15u) : 16;
       return ka < kb;
     });
     ChunkRec cr;
@@ -381,7 +381,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       SubGroup& sg = subs[si];
       if (sg.kind_a) {
         ++ng_a;
-        cr.a_cnt[(sg.G.meta >> 24) & 7u]++;
+        cr.a_cnt[(sg.G.meta >> 24) & 15u]++;
       }
       sg.G.meta |= (uint32_t)pl;
       for (size_t j = 0; j < sg.pats.size(); ++j) {
