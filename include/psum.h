@@ -50,8 +50,10 @@ int psum_create(int n_qubits, int64_t n_terms, const uint64_t* x_mask, const uin
                 const uint8_t* ypow, const double* coeff_re_im, psum_handle_t* out);
 int psum_destroy(psum_handle_t h);
 
-/* Tuning/testing knobs (before first use): "tile_bits" (8..13), "low_bits" (1..6),
- * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover". */
+/* Tuning/testing knobs (before first use): "tile_bits" (11..13), "low_bits" (1..8),
+ * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover";
+ * "lanczos_probe" (0 off, 1 on, 2 auto): after the k lowest pairs converged, lock them and probe
+ * the complement with a fresh random direction so that degenerate copies are found. */
 int psum_set_option(psum_handle_t h, const char* key, int64_t value);
 
 /* info[0]=n_qubits [1]=merged terms [2]=distinct x-masks (G_x) [3]=passes [4]=groups read from

@@ -114,6 +114,7 @@ struct psum_handle_s {
   std::vector<MergedTerm> terms;
   bool hermitian = true, diagonal = true;
   PlanOptions opt;
+  int lanczos_probe = 2;  // 0 off, 1 on, 2 auto (on for <= 2^20 amplitudes per rank)
   std::vector<PartHost> parts;
   bool planned = false;
   // device side
@@ -322,6 +323,10 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "min_cover") {
     if (value < 1) return fail(PSUM_ERR_INVALID, "min_cover must be >= 1");
     h->opt.min_cover = (int)value;
+  } else if (k == "lanczos_probe") {
+    if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "lanczos_probe must be 0, 1 or 2");
+    h->lanczos_probe = (int)value;
+    return PSUM_OK;
   } else {
     return fail(PSUM_ERR_INVALID, "unknown option %s", key);
   }

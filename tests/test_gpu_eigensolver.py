@@ -88,3 +88,30 @@ def test_config3_molecular_k4():
     assert abs(r['evals'][0] - ev[0]) < 1e-9
     assert abs(round(r['evals'][0] + g['nuclear_repulsion'], 3) - g['expect_total_energy_3dp']) < 1.5e-3
     assert r['resid'].max() < 1e-7
+
+
+def test_lanczos_finds_degenerate_copies():
+    """Exact degeneracies: a single-vector Krylov space sees each eigenvalue once; the probe
+    restarts must recover the multiplicities the reference's dense/ARPACK path reports.
+    Ferromagnetic Heisenberg ring, 6 sites: spectrum -6 (x7), -4 (x...), ..."""
+    n = 6
+    labels, coeffs = [], []
+    for i in range(n):
+        for P in 'XYZ':
+            lab = ['I'] * n
+            lab[i] = P
+            lab[(i + 1) % n] = P
+            labels.append(''.join(lab))
+            coeffs.append(-1.0)
+    eng = PauliSumEngine.from_labels(labels, coeffs)
+    terms = list(zip(coeffs, labels))
+    ev = np.linalg.eigvalsh(po.ref_to_spmatrix(terms).toarray())
+    assert abs(ev[0] - ev[6]) < 1e-10 and ev[7] - ev[6] > 1.0          # 7-fold ground multiplet
+    r = eng.lanczos(k=9, tol=1e-12, want_residuals=True)
+    np.testing.assert_allclose(r['evals'], ev[:9], rtol=0, atol=1e-9)
+    vecs = r['evecs'].cpu().numpy()
+    np.testing.assert_allclose(np.abs(vecs @ vecs.conj().T), np.eye(9), atol=1e-8)
+    assert r['resid'].max() < 1e-8
+    eng.set_option('lanczos_probe', 0)
+    r0 = eng.lanczos(k=3, tol=1e-12)
+    assert abs(r0['evals'][0] - ev[0]) < 1e-9           # the lowest value never needs the probe
