@@ -323,6 +323,9 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "min_cover") {
     if (value < 1) return fail(PSUM_ERR_INVALID, "min_cover must be >= 1");
     h->opt.min_cover = (int)value;
+  } else if (k == "plan_tries") {
+    if (value < 1 || value > 4096) return fail(PSUM_ERR_INVALID, "plan_tries must be 1..4096");
+    h->opt.plan_tries = (int)value;
   } else if (k == "lanczos_probe") {
     if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "lanczos_probe must be 0, 1 or 2");
     h->lanczos_probe = (int)value;

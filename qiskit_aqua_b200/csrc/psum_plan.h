@@ -118,6 +118,7 @@ struct PlanOptions {
   int tile_bits = 12;
   int low_bits = 4;
   int min_cover = 3;
+  int plan_tries = 8;   // randomised greedy restarts of the pass planner; the cheapest plan wins
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
 };
 
@@ -167,8 +168,16 @@ struct PassChoice {
 };
 
 inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks, int n_loc, int L,
-                                             int c, int min_cover) {
+                                             int c, int min_cover, uint64_t seed = 0) {
   std::vector<PassChoice> passes;
+  uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  auto noise = [&]() {  // seed 0 -> deterministic greedy; otherwise scores are jittered by <= 40 %
+    if (seed == 0) return 1.0;
+    rng ^= rng << 13;
+    rng ^= rng >> 7;
+    rng ^= rng << 17;
+    return 1.0 + 0.4 * (double)(rng >> 11) * (1.0 / 9007199254740992.0);
+  };
   L = std::min(L, n_loc);
   c = std::min(c, L);
   const uint64_t low = low_mask(c);
@@ -199,6 +208,7 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
       }
       if (!any) break;
       int best = -1;
+      for (int b = 0; b < n_loc; ++b) score[b] *= noise();
       for (int b = 0; b < n_loc; ++b)
         if (!(S >> b & 1ull) && (best < 0 || score[b] > score[best])) best = b;
       if (best < 0 || score[best] <= 0.0) break;
@@ -465,7 +475,22 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
     // tiled plan (kernel B)
     if (n_loc >= 11 && opt.kernel != 1) {
       int L = std::max(11, std::min({opt.tile_bits, kMaxTileBits, n_loc}));
-      std::vector<PassChoice> pcs = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover);
+      // cost of a plan in units of 16 N bytes of HBM traffic: a pass reads psi and reads+writes
+      // y (3 units), a remote group re-reads one partner vector (1 unit)
+      std::vector<PassChoice> pcs;
+      long best_cost = -1;
+      for (int t = 0; t < std::max(1, opt.plan_tries); ++t) {
+        std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t);
+        long n_remote = 0;
+        for (auto& pc : cand)
+          for (int mi : pc.members)
+            if (masks[mi] & ~pc.free_mask) ++n_remote;
+        const long cost = 3 * (long)cand.size() + n_remote;
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          pcs.swap(cand);
+        }
+      }
       for (auto& pc : pcs) P.passes.push_back(build_pass(P.comp, tom, masks, pc, n_loc));
     }
     out.push_back(std::move(P));

@@ -586,6 +586,13 @@ class VectorStateFn(StateFnBase):
     def mul(self, scalar):
         return VectorStateFn(self._dev, self.coeff * scalar, self.is_measurement)
 
+    def add(self, other):
+        if not isinstance(other, VectorStateFn):
+            other = StateFn(other)
+        if other.is_measurement != self.is_measurement:
+            raise ValueError('cannot add a state and a measurement')
+        return VectorStateFn(self._dev * self.coeff + other._dev * other.coeff, 1.0, self.is_measurement)
+
     def adjoint(self):
         return VectorStateFn(self._dev, np.conj(self.coeff), not self.is_measurement)
 
@@ -668,6 +675,14 @@ def StateFn(primitive, coeff=1.0, is_measurement=False):
     """Factory (state_fns/state_fn.py:47-92): vectors -> VectorStateFn, operators -> OperatorStateFn."""
     if isinstance(primitive, (VectorStateFn, OperatorStateFn)):
         return primitive
+    if isinstance(primitive, str):                 # basis state '0101' (state_fn.py:66-71)
+        primitive = {primitive: 1.0}
+    if isinstance(primitive, dict):                # DictStateFn: {bitstring: amplitude}, index = int(b, 2)
+        n = len(next(iter(primitive)))             # (state_fns/dict_state_fn.py:148-157)
+        vec = np.zeros(1 << n, dtype=np.complex128)
+        for bits, amp in primitive.items():
+            vec[int(bits, 2)] += amp
+        primitive = vec
     if isinstance(primitive, (_PauliSumMixin, WeightedPauliOperator)):
         if isinstance(primitive, WeightedPauliOperator):
             primitive = primitive.to_opflow()

@@ -118,6 +118,9 @@ def test_state_overlaps_g6():
     psi[0] += 3 + .1j
     sf = StateFn(psi)
     assert abs((~sf).eval(sf) - 14.45) < 1e-12
+    # the reference builds it from dict states: 4*{'101010': .5, '111111': .3} + (3+.1j)*Zero^6
+    sf2 = 4 * StateFn({'101010': .5, '111111': .3}) + (3 + .1j) * StateFn('000000')
+    assert abs((~sf2).eval(sf2) - 14.45) < 1e-12
     ghz = np.zeros(16, dtype=complex)
     ghz[0] = ghz[15] = 1 / np.sqrt(2)
     assert abs((~StateFn(X ^ 4) @ StateFn(ghz)).eval() - 1) < 1e-12
