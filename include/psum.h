@@ -100,6 +100,14 @@ int psum_lanczos(psum_handle_t h, int k, double tol, int max_iter, uint64_t seed
                  int64_t mem_budget_bytes, double* evals, void* evecs_dev, double* resid_out,
                  int* iters_out, psum_stream_t stream);
 
+/* ---- time evolution on the matvec: out = exp(-i t H) psi ("next" row of SURVEY 8f) ----------
+ * Replaces the exact branch of MatrixOperator.evolve (legacy/matrix_operator.py:354-355) and
+ * MatrixEvolution (evolutions/matrix_evolution.py:32-63) with Krylov (Lanczos) exponentiation:
+ * krylov_dim basis vectors (0 = auto), adaptive sub-steps with local error <= tol.  out_dev may
+ * equal psi_dev.  Hermitian sums only. */
+int psum_evolve(psum_handle_t h, const void* psi_dev, void* out_dev, double t, double tol,
+                int krylov_dim, int* steps_out, int* matvecs_out, psum_stream_t stream);
+
 /* ---- vector helpers used by the host-side callers (device pointers, complex128) -------- */
 /* Counter-based synthetic state: psi[i] = gauss(seed, first_index + i); its CPU twin is
  * oracle/psum_oracle.c:psum_oracle_state.  Not normalised. */

@@ -31,6 +31,8 @@ SIGNATURES = {
     'psum_diag_kmin': (C.c_int, [_vp, C.c_int, _dp, _u64p, _vp]),
     'psum_lanczos': (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int64, _dp, _vp,
                                _dp, C.POINTER(C.c_int), _vp]),
+    'psum_evolve': (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int),
+                              C.POINTER(C.c_int), _vp]),
     'psum_fill_state': (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]),
     'psum_vec_dot': (C.c_int, [_vp, _vp, C.c_uint64, _dp, _vp]),
     'psum_vec_scale': (C.c_int, [_vp, C.c_uint64, C.c_double, C.c_double, _vp]),

@@ -196,6 +196,18 @@ class PauliSumEngine:
         return {'evals': np.array(ev[:]), 'evecs': vecs,
                 'resid': np.array(rs[:]) if want_residuals else None, 'iters': it.value}
 
+    # -- time evolution ------------------------------------------------------------------------------
+    def evolve(self, psi, t, tol=1e-10, krylov_dim=0, out=None):
+        """exp(-i t H) psi on the device (legacy/matrix_operator.py:354-355 without the matrix).
+        Returns (state tensor, info dict)."""
+        psi = as_device_state(psi, self.n_local_amps)
+        if out is None:
+            out = torch.empty_like(psi)
+        steps, mv = C.c_int(0), C.c_int(0)
+        check(lib().psum_evolve(self._h, C.c_void_p(psi.data_ptr()), C.c_void_p(out.data_ptr()), float(t),
+                                float(tol), int(krylov_dim), C.byref(steps), C.byref(mv), _stream_ptr()))
+        return out, {'steps': steps.value, 'matvecs': mv.value}
+
     # -- sharding -------------------------------------------------------------------------------------
     def shard(self, rank, world, unique_id=None):
         buf = None

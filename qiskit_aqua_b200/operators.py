@@ -356,6 +356,19 @@ class WeightedPauliOperator(LegacyBaseOperator):
         psi = as_device_state(quantum_state, 1 << self.num_qubits)
         return self.engine.expect(psi), 0.0
 
+    def evolve(self, state_in, evo_time=0, num_time_slices=0, tol=1e-10):
+        """exp(-i * evo_time * H) @ state_in -- the exact branch (num_time_slices == 0) of
+        MatrixOperator.evolve (legacy/matrix_operator.py:319-355), by Krylov exponentiation on the
+        device.  Returns a numpy array for numpy input, else a CUDA tensor."""
+        if self.is_empty():
+            raise AquaError('Operator is empty, check the operator.')
+        if num_time_slices < 0 or not isinstance(num_time_slices, int):
+            raise ValueError('Number of time slices should be a non-negative integer.')
+        if num_time_slices != 0:
+            raise ValueError('only the exact evolution (num_time_slices=0) is provided on this path')
+        out, _ = self.engine.evolve(state_in, float(np.real(evo_time)), tol=tol)
+        return out if hasattr(state_in, 'is_cuda') else out.cpu().numpy()
+
     def to_opflow(self, reverse_endianness=False):
         """SummedOp of PauliOps (reference :96-117)."""
         ops = []
