@@ -108,6 +108,16 @@ int psum_lanczos(psum_handle_t h, int k, double tol, int max_iter, uint64_t seed
 int psum_evolve(psum_handle_t h, const void* psi_dev, void* out_dev, double t, double tol,
                 int krylov_dim, int* steps_out, int* matvecs_out, psum_stream_t stream);
 
+/* ---- ansatz -> psi on the device ("next" row 1 of SURVEY 8f; single GPU) -------------------
+ * The step right before the hot path in VQE: the reference obtains psi from a simulator backend
+ * (converters/circuit_sampler.py:330-333) and copies 2^n amplitudes per evaluation.  These three
+ * calls let a host-side circuit description prepare psi in place on the device instead. */
+int psum_state_basis(void* psi_dev, int n_qubits, uint64_t index, psum_stream_t stream);
+/* u_re_im: row-major 2x2 complex matrix {u00, u01, u10, u11} as 8 doubles, applied to qubit q. */
+int psum_gate_1q(void* psi_dev, int n_qubits, int q, const double* u_re_im, psum_stream_t stream);
+/* kind 0 = CX(control, target), 1 = CZ(control, target). */
+int psum_gate_2q(void* psi_dev, int n_qubits, int kind, int control, int target, psum_stream_t stream);
+
 /* ---- vector helpers used by the host-side callers (device pointers, complex128) -------- */
 /* Counter-based synthetic state: psi[i] = gauss(seed, first_index + i); its CPU twin is
  * oracle/psum_oracle.c:psum_oracle_state.  Not normalised. */

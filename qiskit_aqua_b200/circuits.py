@@ -1,0 +1,175 @@
+"""Ansatz -> psi on the device ("next" row 1).
+
+A tiny circuit description (RY/RZ/RX/H/X/CX/CZ) executed gate by gate on a complex128 CUDA
+tensor through libpsum.so, so a VQE-style energy evaluation  E(theta) = <psi(theta)|H|psi(theta)>
+never moves 2^n amplitudes over PCIe.  Stands in for the simulator call inside
+CircuitSampler (reference converters/circuit_sampler.py:240-342, :330-333) and the
+RealAmplitudes / EfficientSU2 ansatz circuits used by the reference's VQE tests
+(test/aqua/test_vqe.py:34-55).  Qubit q <-> bit q of the basis index (terra ordering).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .engine import _stream_ptr
+
+
+def _u(name, theta=0.0):
+    c, s = math.cos(theta / 2), math.sin(theta / 2)
+    if name == 'ry':
+        return [[c, -s], [s, c]]
+    if name == 'rx':
+        return [[c, -1j * s], [-1j * s, c]]
+    if name == 'rz':
+        return [[complex(c, -s), 0], [0, complex(c, s)]]
+    if name == 'h':
+        r = 1 / math.sqrt(2)
+        return [[r, r], [r, -r]]
+    if name == 'x':
+        return [[0, 1], [1, 0]]
+    raise ValueError('unknown gate %s' % name)
+
+
+class StatevectorCircuit:
+    """Ordered gate list; parameters are either numbers or integer indices into a vector."""
+
+    def __init__(self, num_qubits):
+        self.num_qubits = int(num_qubits)
+        self.gates = []          # (name, qubits, value or ('p', index))
+        self.num_parameters = 0
+
+    def _add(self, name, qubits, value=None):
+        self.gates.append((name, tuple(qubits), value))
+        return self
+
+    def new_parameter(self):
+        self.num_parameters += 1
+        return ('p', self.num_parameters - 1)
+
+    def ry(self, theta, q):
+        return self._add('ry', [q], theta)
+
+    def rx(self, theta, q):
+        return self._add('rx', [q], theta)
+
+    def rz(self, theta, q):
+        return self._add('rz', [q], theta)
+
+    def h(self, q):
+        return self._add('h', [q])
+
+    def x(self, q):
+        return self._add('x', [q])
+
+    def cx(self, c, t):
+        return self._add('cx', [c, t])
+
+    def cz(self, c, t):
+        return self._add('cz', [c, t])
+
+    def run(self, params=None, out=None):
+        """Executes on |0...0> and returns the complex128 CUDA state tensor."""
+        n = self.num_qubits
+        if params is None:
+            params = []
+        if len(params) != self.num_parameters:
+            raise ValueError('expected %d parameters, got %d' % (self.num_parameters, len(params)))
+        if out is None:
+            out = torch.empty(1 << n, dtype=torch.complex128, device='cuda')
+        L = lib()
+        ptr, st = C.c_void_p(out.data_ptr()), _stream_ptr()
+        check(L.psum_state_basis(ptr, n, 0, st))
+        buf = (C.c_double * 8)()
+        for name, qs, val in self.gates:
+            if name in ('cx', 'cz'):
+                check(L.psum_gate_2q(ptr, n, 0 if name == 'cx' else 1, qs[0], qs[1], st))
+                continue
+            theta = 0.0 if val is None else (params[val[1]] if isinstance(val, tuple) else val)
+            u = np.asarray(_u(name, float(theta)), dtype=np.complex128).reshape(4)
+            for i in range(4):
+                buf[2 * i], buf[2 * i + 1] = u[i].real, u[i].imag
+            check(L.psum_gate_1q(ptr, n, qs[0], buf, st))
+        return out
+
+
+def _entangler_pairs(n, entanglement):
+    if entanglement == 'linear':
+        return [(i, i + 1) for i in range(n - 1)]
+    if entanglement == 'full':
+        return [(i, j) for i in range(n) for j in range(i + 1, n)]
+    if entanglement == 'circular':
+        return ([(n - 1, 0)] if n > 2 else []) + [(i, i + 1) for i in range(n - 1)]
+    raise ValueError('unknown entanglement %r' % entanglement)
+
+
+class RealAmplitudes(StatevectorCircuit):
+    """RY layers + CX entanglers (terra circuit library RealAmplitudes, parameter order
+    theta[layer * n + qubit])."""
+
+    def __init__(self, num_qubits, reps=3, entanglement='full'):
+        super().__init__(num_qubits)
+        for layer in range(reps + 1):
+            for q in range(num_qubits):
+                self.ry(self.new_parameter(), q)
+            if layer < reps:
+                for c, t in _entangler_pairs(num_qubits, entanglement):
+                    self.cx(c, t)
+
+
+class EfficientSU2(StatevectorCircuit):
+    """RY + RZ layers + CX entanglers (parameter order: all RY of a layer, then all RZ)."""
+
+    def __init__(self, num_qubits, reps=3, entanglement='full'):
+        super().__init__(num_qubits)
+        for layer in range(reps + 1):
+            for q in range(num_qubits):
+                self.ry(self.new_parameter(), q)
+            for q in range(num_qubits):
+                self.rz(self.new_parameter(), q)
+            if layer < reps:
+                for c, t in _entangler_pairs(num_qubits, entanglement):
+                    self.cx(c, t)
+
+
+class CircuitStateFn:
+    """state_fns/circuit_state_fn.py stand-in: a state defined by a bound circuit; evaluating it
+    prepares psi on the device."""
+
+    def __init__(self, circuit, params=None, coeff=1.0):
+        self.circuit, self.params, self.coeff = circuit, params, coeff
+        self.is_measurement = False
+
+    @property
+    def num_qubits(self):
+        return self.circuit.num_qubits
+
+    def bind_parameters(self, params):
+        return CircuitStateFn(self.circuit, params, self.coeff)
+
+    def to_vector_state_fn(self):
+        from .operators import VectorStateFn
+        return VectorStateFn(self.circuit.run(self.params), coeff=self.coeff)
+
+    def device_vector(self):
+        return self.circuit.run(self.params)
+
+    def eval(self, front=None):
+        return self.to_vector_state_fn()
+
+
+def energy_evaluation(operator, ansatz, parameters):
+    """VQE._energy_evaluation (reference algorithms/minimum_eigen_solvers/vqe.py:496-541) for a
+    statevector backend: parameters may hold several concatenated parameter sets
+    (max_evals_grouped, vqe.py:518); returns the real means, one per set, computed entirely on
+    the device."""
+    p = np.asarray(parameters, dtype=float).reshape(-1, ansatz.num_parameters)
+    eng = operator.engine if hasattr(operator, 'engine') else operator._engine_for()
+    out = []
+    buf = None
+    for row in p:
+        buf = ansatz.run(row, out=buf)
+        out.append(eng.expect(buf).real)
+    return out[0] if len(out) == 1 else np.array(out)

@@ -639,6 +639,41 @@ extern "C" int psum_vec_axpy(void* y_dev, const void* x_dev, uint64_t n_amps, do
 }
 
 // ---------------------------------------------------------------------------------------------
+// gate-level state preparation (single GPU)
+// ---------------------------------------------------------------------------------------------
+extern "C" int psum_state_basis(void* psi_dev, int n_qubits, uint64_t index, psum_stream_t stream) {
+  if (!psi_dev || n_qubits < 1 || n_qubits > 40) return fail(PSUM_ERR_INVALID, "bad argument");
+  const uint64_t N = 1ull << n_qubits;
+  if (index >= N) return fail(PSUM_ERR_INVALID, "basis index out of range");
+  k_set_basis_state<<<vec_grid(N), kThreads, 0, (cudaStream_t)stream>>>((double2*)psi_dev, N, index);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+extern "C" int psum_gate_1q(void* psi_dev, int n_qubits, int q, const double* u_re_im, psum_stream_t stream) {
+  if (!psi_dev || !u_re_im || n_qubits < 1 || q < 0 || q >= n_qubits) return fail(PSUM_ERR_INVALID, "bad argument");
+  Gate2x2 U;
+  U.u00 = make_double2(u_re_im[0], u_re_im[1]);
+  U.u01 = make_double2(u_re_im[2], u_re_im[3]);
+  U.u10 = make_double2(u_re_im[4], u_re_im[5]);
+  U.u11 = make_double2(u_re_im[6], u_re_im[7]);
+  const uint64_t pairs = 1ull << (n_qubits - 1);
+  k_gate_1q<<<vec_grid(pairs), kThreads, 0, (cudaStream_t)stream>>>((double2*)psi_dev, pairs, q, U);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+extern "C" int psum_gate_2q(void* psi_dev, int n_qubits, int kind, int control, int target, psum_stream_t stream) {
+  if (!psi_dev || n_qubits < 2 || control < 0 || target < 0 || control >= n_qubits || target >= n_qubits ||
+      control == target || kind < 0 || kind > 1)
+    return fail(PSUM_ERR_INVALID, "bad argument");
+  const uint64_t quads = 1ull << (n_qubits - 2);
+  k_gate_cx_cz<<<vec_grid(quads), kThreads, 0, (cudaStream_t)stream>>>((double2*)psi_dev, quads, control, target, kind);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // sharding
 // ---------------------------------------------------------------------------------------------
 extern "C" int psum_nccl_unique_id(void* out128) {

@@ -566,6 +566,55 @@ k_reduce_rows(const double2* __restrict__ partial, int cols, double2* __restrict
   if (threadIdx.x == 0) out[blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------------------------------
+// gate-level state preparation (ansatz -> psi on the device, "next" row 1 of SURVEY 8f)
+// ------------------------------------------------------------------------------------------
+struct Gate2x2 {
+  double2 u00, u01, u10, u11;
+};
+// psi <- (U on qubit q) psi ; one thread per amplitude pair
+__global__ void k_gate_1q(double2* __restrict__ psi, uint64_t n_pairs, int q, Gate2x2 U) {
+  const uint64_t low = (1ull << q) - 1ull;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
+       p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i0 = ((p & ~low) << 1) | (p & low);
+    const uint64_t i1 = i0 | (1ull << q);
+    const double2 a = psi[i0], b = psi[i1];
+    double2 r0, r1;
+    r0.x = U.u00.x * a.x - U.u00.y * a.y + U.u01.x * b.x - U.u01.y * b.y;
+    r0.y = U.u00.x * a.y + U.u00.y * a.x + U.u01.x * b.y + U.u01.y * b.x;
+    r1.x = U.u10.x * a.x - U.u10.y * a.y + U.u11.x * b.x - U.u11.y * b.y;
+    r1.y = U.u10.x * a.y + U.u10.y * a.x + U.u11.x * b.y + U.u11.y * b.x;
+    psi[i0] = r0;
+    psi[i1] = r1;
+  }
+}
+// controlled-X (swap) or controlled-Z (sign) on the quarter of the amplitudes with control = 1
+__global__ void k_gate_cx_cz(double2* __restrict__ psi, uint64_t n_quads, int c, int t, int is_cz) {
+  const int lo = c < t ? c : t, hi = c < t ? t : c;
+  const uint64_t mlo = (1ull << lo) - 1ull, mhi = (1ull << (hi - 1)) - 1ull;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_quads;
+       p += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = ((p & ~mlo) << 1) | (p & mlo);     // insert a 0 at bit lo
+    i = ((i & ~((mhi << 1) | 1ull)) << 1) | (i & ((mhi << 1) | 1ull));  // insert a 0 at bit hi
+    const uint64_t i10 = i | (1ull << c);           // control 1, target 0
+    const uint64_t i11 = i10 | (1ull << t);
+    if (is_cz) {
+      double2 v = psi[i11];
+      psi[i11] = make_double2(-v.x, -v.y);
+    } else {
+      const double2 a = psi[i10], b = psi[i11];
+      psi[i10] = b;
+      psi[i11] = a;
+    }
+  }
+}
+__global__ void k_set_basis_state(double2* __restrict__ psi, uint64_t n_amps, uint64_t index) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    psi[i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
+}
+
 // diagonal of an all-Z sum: d[i] = sum_k re_k (-1)^{popc(i & z_k)}
 __global__ void k_diag(double* __restrict__ d, const SimpleTerm* __restrict__ terms, int nterms,
                        uint64_t n_amps, uint64_t first_index_sign_mask_unused) {

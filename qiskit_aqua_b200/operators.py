@@ -688,6 +688,8 @@ def StateFn(primitive, coeff=1.0, is_measurement=False):
     """Factory (state_fns/state_fn.py:47-92): vectors -> VectorStateFn, operators -> OperatorStateFn."""
     if isinstance(primitive, (VectorStateFn, OperatorStateFn)):
         return primitive
+    if hasattr(primitive, 'to_vector_state_fn'):   # CircuitStateFn: prepare psi on the device
+        return primitive.to_vector_state_fn()
     if isinstance(primitive, str):                 # basis state '0101' (state_fn.py:66-71)
         primitive = {primitive: 1.0}
     if isinstance(primitive, dict):                # DictStateFn: {bitstring: amplitude}, index = int(b, 2)
