@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpsum.so')
+LIB_PATH = os.environ.get('PSUM_LIB_PATH') or os.path.join(HERE, 'libpsum.so')  # override: kernel-variant experiments
 
 PSUM_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_EMPTY, ERR_NOT_HERMITIAN, ERR_NOT_DIAGONAL, ERR_NCCL, ERR_NOMEM, \

@@ -133,6 +133,10 @@ __device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, in
 //   IM    : the pass has imaginary component patterns (complex D); real-only passes carry half
 //           the class accumulators
 //   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
+#ifndef PSUM_LOOPA_UNROLL
+#define PSUM_LOOPA_UNROLL 2
+#endif
+constexpr int kLoopAUnroll = PSUM_LOOPA_UNROLL;
 #ifndef PSUM_MIN_CTAS
 #define PSUM_MIN_CTAS 2
 #endif
@@ -246,6 +250,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
           for (int cls = 0; cls < (IM ? 16 : 8); ++cls) {
             const int gend = g + (int)(((cls < 8 ? acnt_re : acnt_im) >> (8 * (cls & 7))) & 0xffull);
+#pragma unroll(kLoopAUnroll)
             for (; g < gend; ++g) {
               const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
               const uint32_t tp = t0 ^ h0.x;
