@@ -455,6 +455,8 @@ static int apply_local(psum_handle_s* h, const double2* psi, const double2* bra,
   if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
   if (!psi || (!y && !expect_out)) return fail(PSUM_ERR_INVALID, "null device pointer");
   if (y == psi) return fail(PSUM_ERR_INVALID, "y must not alias psi");
+  if (((uintptr_t)psi | (uintptr_t)y | (uintptr_t)bra) & 15u)
+    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
   PS_TRY(upload(h));
   size_t pcount = 0;
   for (const DevPart& D : h->dparts)
@@ -733,6 +735,8 @@ extern "C" int psum_apply_part(psum_handle_t h, int g, const void* src_dev, cons
                                int accumulate, double* expect_acc, psum_stream_t stream) {
   if (!h || !src_dev) return fail(PSUM_ERR_INVALID, "null argument");
   if (!y_dev && !expect_acc) return fail(PSUM_ERR_INVALID, "nothing to compute");
+  if (((uintptr_t)src_dev | (uintptr_t)y_dev | (uintptr_t)bra_dev) & 15u)
+    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
   PS_TRY(upload(h));
   cudaStream_t st = (cudaStream_t)stream;
   const DevPart* D = nullptr;
@@ -780,6 +784,8 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
   if (!h || !psi_dev) return fail(PSUM_ERR_INVALID, "null argument");
   if (!y_dev && !expect_out) return fail(PSUM_ERR_INVALID, "nothing to compute");
   if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if (((uintptr_t)psi_dev | (uintptr_t)y_dev | (uintptr_t)recv_dev) & 15u)
+    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
   PS_TRY(upload(h));
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t N = n_local_amps(h);
