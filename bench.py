@@ -146,7 +146,7 @@ def run_reference(args):
     _, x, z, y, c = workload(n_total, args.workload)
     T = len(x)
     psi = co.counter_state(30, 0, 1 << n_cpu)
-    rows = 1 << 20
+    rows = min(1 << 20, 1 << n_cpu)
     xs, zs, ys, cs = x & np.uint64((1 << n_cpu) - 1), z & np.uint64((1 << n_cpu) - 1), y, c
     times = []
     for s in range(args.warmup + args.steps):

@@ -495,19 +495,18 @@ extern "C" int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev
   if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
   PS_TRY(upload(h));
   cudaStream_t st = (cudaStream_t)stream;
-  if (batch > 256) return fail(PSUM_ERR_INVALID, "batch > 256");
   const double2* base = (const double2*)psi_dev;
-  size_t stride_partials = 0;
-  for (int b = 0; b < batch; ++b) {
-    const double2* psi = base + (uint64_t)b * n_local_amps(h);
-    size_t pcount = 0;
-    for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st));
-    stride_partials = pcount;
-    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar + b, 0);
+  for (int b0 = 0; b0 < batch; b0 += 256) {          // 256 device scalars per round trip
+    const int nb = std::min(256, batch - b0);
+    for (int b = 0; b < nb; ++b) {
+      const double2* psi = base + (uint64_t)(b0 + b) * n_local_amps(h);
+      size_t pcount = 0;
+      for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st));
+      k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar + b, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    PS_TRY(fetch_scalars(h, nb, out + 2 * b0, st));
   }
-  (void)stride_partials;
-  CUDA_TRY(cudaGetLastError());
-  if (batch) PS_TRY(fetch_scalars(h, batch, out, st));
   return PSUM_OK;
 }
 

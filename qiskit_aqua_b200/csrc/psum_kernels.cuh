@@ -57,19 +57,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-__device__ __forceinline__ void wht8(double* v) {
-#pragma unroll
-  for (int h = 1; h < 8; h <<= 1)
-#pragma unroll
-    for (int i = 0; i < 8; i += 2 * h)
-#pragma unroll
-      for (int j = i; j < i + h; ++j) {
-        double a = v[j], b = v[j + h];
-        v[j] = a + b;
-        v[j + h] = a - b;
-      }
-}
-
 // deterministic block reduction of a complex value; result valid in thread 0
 __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
 #pragma unroll
@@ -102,16 +89,6 @@ __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
     _Pragma("unroll") for (int r = 0; r < 8; ++r) {              \
       if (__popc(r & ((C) & 7)) & 1) D[((C) >> 3) * 8 + r] -= s; \
       else D[((C) >> 3) * 8 + r] += s;                           \
-    }                                                            \
-  } break;
-
-// yacc[r] += (s0 + (-1)^{popc(r & C)} s1) * pv[r]  with C the compile-time class of slot 1
-#define PSUM_PAIR_CASE(C)                                        \
-  case C: {                                                      \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) {              \
-      const double d = (__popc(r & (C)) & 1) ? dm : dp;          \
-      yacc[r].x = fma(d, pv[r].x, yacc[r].x);                    \
-      yacc[r].y = fma(d, pv[r].y, yacc[r].y);                    \
     }                                                            \
   } break;
 
@@ -374,7 +351,6 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   }
 }
 #undef PSUM_CLASS_CASE
-#undef PSUM_PAIR_CASE
 
 // ------------------------------------------------------------------------------------------
 // Kernel A: streaming form, one amplitude per thread (grid-stride).  Any n_loc >= 0.
