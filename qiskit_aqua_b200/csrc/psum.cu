@@ -97,6 +97,7 @@ int load_nccl() {
 struct DevPass {
   PassParams params;
   bool has_im = false;
+  int threads = 256;
   int grid = 0;
   size_t smem = 0;
 };
@@ -156,7 +157,7 @@ static int plan(psum_handle_s* h) {
 
 static size_t pass_smem_bytes(int L) {
   return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * (kGrpChunk + 1) +
-         16 * (kThreads / 32) + 8 * 9 * 64;
+         16 * 16 + 8 * 9 * 64;
 }
 
 template <typename T>
@@ -229,6 +230,7 @@ static int upload(psum_handle_s* h) {
         }
         dp.has_im = ph.has_im;
         dp.smem = pass_smem_bytes(ph.L);
+        dp.threads = ph.L >= 13 ? 512 : 256;   // 2^13 tiles: one 512-thread CTA per SM
         int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
         dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
         pass_partials += dp.grid;
@@ -252,8 +254,9 @@ static int upload(psum_handle_s* h) {
   static bool attr_done = false;
   if (!attr_done) {
     int max_smem = (int)pass_smem_bytes(kMaxTileBits);
-#define SET_SMEM(S, E, I) \
-  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define SET_SMEM(S, E, I)                                                                              \
+  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SET_SMEM(true, true, true) SET_SMEM(true, true, false) SET_SMEM(true, false, true)
     SET_SMEM(true, false, false) SET_SMEM(false, true, true) SET_SMEM(false, true, false)
 #undef SET_SMEM
@@ -413,7 +416,11 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
       const double2* b = bra_is_src ? nullptr : bra;
       if (ex && *pcount + dp.grid > h->partial_cap)
         return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
-#define LAUNCH(S, E, I) k_pass<S, E, I><<<dp.grid, kThreads, dp.smem, st>>>(src, b, y, pp, part)
+#define LAUNCH(S, E, I)                                                                     \
+  do {                                                                                      \
+    if (dp.threads == 512) k_pass<S, E, I, 512><<<dp.grid, 512, dp.smem, st>>>(src, b, y, pp, part); \
+    else k_pass<S, E, I, 256><<<dp.grid, 256, dp.smem, st>>>(src, b, y, pp, part);            \
+  } while (0)
       if (dp.has_im) {
         if (y && ex) LAUNCH(true, true, true);
         else if (y) LAUNCH(true, false, true);

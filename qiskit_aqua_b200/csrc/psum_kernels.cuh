@@ -117,8 +117,9 @@ constexpr int kLoopAUnroll = PSUM_LOOPA_UNROLL;
 #ifndef PSUM_MIN_CTAS
 #define PSUM_MIN_CTAS 2
 #endif
-template <bool STORE, bool EXPECT, bool IM>
-__global__ void __launch_bounds__(kThreads, IM ? 2 : PSUM_MIN_CTAS)
+// NT = threads per CTA: 256 (two CTAs per SM, tiles up to 2^12) or 512 (one CTA per SM, 2^13 tiles)
+template <bool STORE, bool EXPECT, bool IM, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? (IM ? 2 : PSUM_MIN_CTAS) : 1)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
        const PassParams P, double2* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +130,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
   uint4* grp4 = reinterpret_cast<uint4*>(offHi + 32);               // 3 x uint4 per group record
   double2* red = reinterpret_cast<double2*>(grp4 + 3 * (kGrpChunk + 1));
-  uint64_t* baseT = reinterpret_cast<uint64_t*>(red + kThreads / 32);  // [9][64] deposit tables
+  uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,7 +148,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   }
   // tile id -> base index: 6 bits of the tile id per table lookup
   const int nbt = (P.n_nonfree + 5) / 6;
-  for (int e = tid; e < nbt * 64; e += kThreads) {
+  for (int e = tid; e < nbt * 64; e += NT) {
     const int k = e >> 6, v = e & 63;
     uint64_t o = 0;
     for (int j = 0; j < 6 && 6 * k + j < P.n_nonfree; ++j) o |= (uint64_t)((v >> j) & 1) << P.nbit[6 * k + j];
@@ -155,8 +156,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   }
   __syncthreads();
   const uint64_t b5 = 1ull << P.fbit[5], b6 = 1ull << P.fbit[6], b7 = 1ull << P.fbit[7];
-  const int nrounds = (int)(tile_amps / kRoundAmps);
-  const int nload = (int)(tile_amps / kThreads);
+  const int nrounds = (int)(tile_amps / (NT * 8));
+  const int nload = (int)(tile_amps / NT);
   const bool one_chunk = (P.nchunks == 1);
 
   double2 eacc = make_double2(0.0, 0.0);
@@ -166,11 +167,11 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   // one coefficient, stored in pat[] and (first two patterns of a group) inline in its record.
   auto stage_chunk = [&](const ChunkRec ch, uint64_t base) {
     const int ng = ch.ng & 0xffff;
-    for (int g = tid; g < ng * 3; g += kThreads)
+    for (int g = tid; g < ng * 3; g += NT)
       grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
     if (tid < 3) grp4[ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);  // prefetch overrun record
     __syncthreads();
-    for (int p = tid; p < ch.np; p += kThreads) {
+    for (int p = tid; p < ch.np; p += NT) {
       const int gp = ch.p0 + p;
       const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
       double v = 0.0;
@@ -194,14 +195,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 
     __syncthreads();  // previous tile fully consumed
     for (int j = 0; j < nload; ++j)
-      cp_async16(&tile[j * kThreads + tid], &src[base | offLo8 | offHi[j]]);
+      cp_async16(&tile[j * NT + tid], &src[base | offLo8 | offHi[(j * NT + tid) >> 8]]);
     if (one_chunk) stage_chunk(P.chunks[0], base);  // overlaps the tile load
     cp_async_wait_all();
     __syncthreads();
 
     for (int rnd = 0; rnd < nrounds; ++rnd) {
-      const uint32_t t0 = (uint32_t)rnd * kRoundAmps + (uint32_t)warp * 256u + (uint32_t)lane;
-      const uint64_t i0 = base | offLane | offHi[rnd * 8 + warp];
+      const uint32_t t0 = (uint32_t)rnd * (NT * 8) + (uint32_t)warp * 256u + (uint32_t)lane;
+      const uint64_t i0 = base | offLane | offHi[t0 >> 8];
       double2 yacc[8];
       const char* ybase = reinterpret_cast<const char*>(y + i0);
 #pragma unroll
