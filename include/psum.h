@@ -52,6 +52,9 @@ int psum_destroy(psum_handle_t h);
 
 /* Tuning/testing knobs (before first use): "tile_bits" (11..13), "low_bits" (1..8),
  * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover";
+ * "herm_pairing" (1 default): psum_expect of a Hermitian operator evaluates each amplitude pair
+ * (i, i^x) once and doubles it (the imaginary part of the result is then exactly the rounding
+ * noise of a real quantity); 0 forces the generic path.
  * "lanczos_probe" (0 off, 1 on, 2 auto): after the k lowest pairs converged, lock them and probe
  * the complement with a fresh random direction so that degenerate copies are found. */
 int psum_set_option(psum_handle_t h, const char* key, int64_t value);

@@ -116,6 +116,7 @@ struct psum_handle_s {
   bool hermitian = true, diagonal = true;
   PlanOptions opt;
   int lanczos_probe = 2;  // 0 off, 1 on, 2 auto (on for <= 2^20 amplitudes per rank)
+  int herm_pairing = 1;   // <psi|H|psi> of a Hermitian operator: evaluate pairs (i, i^x) once
   std::vector<PartHost> parts;
   bool planned = false;
   // device side
@@ -260,6 +261,10 @@ static int upload(psum_handle_s* h) {
     SET_SMEM(true, true, true) SET_SMEM(true, true, false) SET_SMEM(true, false, true)
     SET_SMEM(true, false, false) SET_SMEM(false, true, true) SET_SMEM(false, true, false)
 #undef SET_SMEM
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_done = true;
   }
   h->uploaded = true;
@@ -329,6 +334,9 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "plan_tries") {
     if (value < 1 || value > 4096) return fail(PSUM_ERR_INVALID, "plan_tries must be 1..4096");
     h->opt.plan_tries = (int)value;
+  } else if (k == "herm_pairing") {
+    h->herm_pairing = value ? 1 : 0;
+    return PSUM_OK;
   } else if (k == "lanczos_probe") {
     if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "lanczos_probe must be 0, 1 or 2");
     h->lanczos_probe = (int)value;
@@ -421,16 +429,26 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
     if (dp.threads == 512) k_pass<S, E, I, 512><<<dp.grid, 512, dp.smem, st>>>(src, b, y, pp, part); \
     else k_pass<S, E, I, 256><<<dp.grid, 256, dp.smem, st>>>(src, b, y, pp, part);            \
   } while (0)
+      // Hermitian pairing: expectation only, <psi|H|psi> of a Hermitian operator, local part
+      const bool herm = !y && h->hermitian && h->herm_pairing && bra_is_src && D.g == 0;
+#define LAUNCH_H(I)                                                                                     \
+  do {                                                                                                  \
+    if (dp.threads == 512) k_pass<false, true, I, 512, true><<<dp.grid, 512, dp.smem, st>>>(src, b, y, pp, part); \
+    else k_pass<false, true, I, 256, true><<<dp.grid, 256, dp.smem, st>>>(src, b, y, pp, part);           \
+  } while (0)
       if (dp.has_im) {
         if (y && ex) LAUNCH(true, true, true);
         else if (y) LAUNCH(true, false, true);
+        else if (herm) LAUNCH_H(true);
         else LAUNCH(false, true, true);
       } else {
         if (y && ex) LAUNCH(true, true, false);
         else if (y) LAUNCH(true, false, false);
+        else if (herm) LAUNCH_H(false);
         else LAUNCH(false, true, false);
       }
 #undef LAUNCH
+#undef LAUNCH_H
       if (ex) *pcount += dp.grid;
     }
   } else {

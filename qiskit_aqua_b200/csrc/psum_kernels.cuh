@@ -118,7 +118,12 @@ constexpr int kLoopAUnroll = PSUM_LOOPA_UNROLL;
 #define PSUM_MIN_CTAS 2
 #endif
 // NT = threads per CTA: 256 (two CTAs per SM, tiles up to 2^12) or 512 (one CTA per SM, 2^13 tiles)
-template <bool STORE, bool EXPECT, bool IM, int NT>
+//   HERM  : (expectation only, Hermitian H, bra == source) a local off-diagonal group whose x has
+//           its highest tile bit among the warp-uniform bits is evaluated only on the half of the
+//           amplitudes with that bit clear, with doubled coefficients: the pair (i, i^x)
+//           contributes z + conj(z) = 2 Re z.  The imaginary part (identically zero for a
+//           Hermitian operator) is returned as exactly 0.
+template <bool STORE, bool EXPECT, bool IM, int NT, bool HERM = false>
 __global__ void __launch_bounds__(NT, NT == 256 ? (IM ? 2 : PSUM_MIN_CTAS) : 1)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
        const PassParams P, double2* __restrict__ partial) {
@@ -177,10 +182,12 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       double v = 0.0;
       for (uint32_t t = ta; t < tb; ++t)
         v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+      const uint32_t zraw = P.pat_zt[gp];
+      if (HERM && (zraw & 0x8000u)) v += v;
       uint4 rec;
       rec.x = (uint32_t)__double2loint(v);
       rec.y = (uint32_t)__double2hiint(v);
-      rec.z = P.pat_zt[gp];
+      rec.z = zraw & 0x7fffu;
       rec.w = 0;
       reinterpret_cast<uint4*>(pat)[p] = rec;
       const uint32_t inl = P.pat_inl[gp];
@@ -231,6 +238,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll(kLoopAUnroll)
             for (; g < gend; ++g) {
               const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+              if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
               const uint32_t tp = t0 ^ h0.x;
               double2 pv[8];
 #pragma unroll
@@ -267,6 +275,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         // ---- loop B: everything else ------------------------------------------------------------
         for (int g = ng_a; g < ng; ++g) {
           const uint4 h0 = grp4[3 * g];
+          if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
           const uint4 h2 = grp4[3 * g + 2];
           const uint32_t xt = h0.x & 0x7fffffffu;
           const bool remote = (h0.x >> 31) != 0;
@@ -347,6 +356,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     }
   }
   if (EXPECT) {
+    if (HERM) eacc.y = 0.0;  // exactly zero for a Hermitian operator; the paired evaluation keeps 2 Re z
     double2 tot = block_reduce(eacc, red);
     if (tid == 0) partial[blockIdx.x] = tot;
   }

@@ -45,6 +45,10 @@ struct GroupRec {     // 48 bytes
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
                       // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry),
                       // bits 24..27 = class (im*8 + zr) of the inline pattern in slot 1 (kind A groups)
+                      // bits 28..31 = hbit: 1 + tile bit (>= 8, i.e. warp-uniform) of the highest
+                      //               set bit of xt for local off-diagonal groups, else 0.  The
+                      //               Hermitian <psi|H|psi> kernels process such a group only for
+                      //               amplitudes with that bit clear and double it (pair i, i^x)
   uint32_t zt0, zt1;  // in-tile z-patterns of the first two patterns (inline copy)
   double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
@@ -270,7 +274,12 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     std::vector<int> rest;
     for (int b : cand)
       if (std::find(reg.begin(), reg.end(), b) == reg.end()) rest.push_back(b);
-    std::sort(rest.begin(), rest.end());
+    // the qubits most often flipped by this pass's x-masks go to the warp-uniform tile bits (8..),
+    // where the Hermitian expectation kernels can skip the partner half of a group
+    std::vector<double> xhits(64, 0.0);
+    for (int mi : pc.members)
+      for (uint64_t m = masks[mi] & S; m; m &= m - 1) xhits[__builtin_ctzll(m)] += 1.0;
+    std::stable_sort(rest.begin(), rest.end(), [&](int a, int b) { return xhits[a] < xhits[b]; });
     int j = 0;
     for (int i = 0; i < std::min(3, L); ++i) P.fbit[j++] = (uint8_t)fb[i];
     size_t ri = 0;
@@ -343,6 +352,13 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       }
       const bool flat = (nent == 1) && (G.ent[0] >> 12) == 0;
       G.meta = ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) | (flat ? (1u << 21) : 0u);
+      {
+        const uint32_t xt_only = G.xt & 0x7fffffffu;
+        if (!remote && xt_only != 0u) {
+          const int msb = 31 - __builtin_clz(xt_only);
+          if (msb >= 8) G.meta |= (uint32_t)(msb + 1) << 28;
+        }
+      }
       // kind A: local, real, at most two patterns, the first (if two) of class 0.  Slot 0 of the
       // inline copy holds the class-0 pattern (or nothing), slot 1 the other one with its class.
       sg.kind_a = !remote && count <= 2 && (count == 1 || pats[p].cls == 0);
@@ -395,7 +411,9 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       }
       sg.G.meta |= (uint32_t)pl;
       for (size_t j = 0; j < sg.pats.size(); ++j) {
-        P.pat_zt.push_back((uint16_t)sg.pats[j].zt);
+        // bit 15 of the stored pattern marks patterns of a Hermitian-paired group (doubled by the
+        // fold of the Hermitian expectation kernels, masked off by every fold)
+        P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | ((sg.G.meta >> 28) ? 0x8000u : 0u)));
         P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
         for (int t : sg.pats[j].terms) {
           P.term_zb.push_back(comp[t].zl & ~S);
