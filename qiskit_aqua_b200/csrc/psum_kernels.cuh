@@ -201,8 +201,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
 
     __syncthreads();  // previous tile fully consumed
-    for (int j = 0; j < nload; ++j)
-      cp_async16(&tile[j * NT + tid], &src[base | offLo8 | offHi[(j * NT + tid) >> 8]]);
+    for (int j = 0; j < nload; ++j) {
+      const uint64_t idx = base | offLo8 | offHi[(j * NT + tid) >> 8];
+      cp_async16(&tile[j * NT + tid], &src[idx]);
+      // the old y of this tile is needed when the rounds start: pull its lines into L2 now
+      // (one prefetch per 128-byte line: 8 amplitudes)
+      if (STORE && P.accumulate && (tid & 7) == 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(y + idx));
+    }
     if (one_chunk) stage_chunk(P.chunks[0], base);  // overlaps the tile load
     cp_async_wait_all();
     __syncthreads();
