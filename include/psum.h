@@ -79,6 +79,12 @@ int psum_apply(psum_handle_t h, const void* psi_dev, void* y_dev, double* expect
  * (state_fns/operator_state_fn.py:179-208) and _eval_aux_operators
  * (algorithms/eigen_solvers/numpy_eigen_solver.py:208-226). */
 int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], psum_stream_t stream);
+/* The same for a state in HOST memory (pinned for full speed): psi_dev is a caller-provided device
+ * buffer of 2^n amplitudes that receives the copy.  The H2D transfer is cut into chunks and the
+ * passes that only combine amplitudes of one chunk run while later chunks are still in flight --
+ * the end-to-end form of evaluate_with_statevector(numpy state). */
+int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi_dev, double out[2],
+                     psum_stream_t stream);
 /* <phi|H|psi> for a different bra (ListOp / transition elements). */
 int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, double out[2],
                    psum_stream_t stream);

@@ -25,6 +25,7 @@ SIGNATURES = {
     'psum_pass_info': (C.c_int, [_vp, C.c_int, C.c_int, _u64p, _i64p, _i64p, _i64p]),
     'psum_apply': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),
     'psum_expect': (C.c_int, [_vp, _vp, _dp, _vp]),
+    'psum_expect_host': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),
     'psum_bra_apply': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),
     'psum_expect_batch': (C.c_int, [_vp, C.c_int, _vp, _dp, _vp]),
     'psum_diag': (C.c_int, [_vp, _vp, _vp]),

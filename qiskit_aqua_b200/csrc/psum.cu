@@ -97,6 +97,7 @@ int load_nccl() {
 struct DevPass {
   PassParams params;
   bool has_im = false;
+  int hi_bit = 0;
   int threads = 256;
   int grid = 0;
   size_t smem = 0;
@@ -128,6 +129,15 @@ struct psum_handle_s {
   size_t partial_cap = 0;
   double2* d_scalar = nullptr;  // 64 complex scalars
   double2* h_scalar = nullptr;  // pinned mirror
+  // chunk-pipelined <psi|H|psi> from host memory (psum_expect_host): its own plan whose early
+  // passes never combine amplitudes of different chunks
+  std::vector<PartHost> parts_h;
+  std::vector<DevPart> dparts_h;
+  void* arena_h = nullptr;
+  int late_bits_h = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[256] = {nullptr};
+  cudaEvent_t ev_free = nullptr;
   // sharding
   nccl_comm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
@@ -138,6 +148,10 @@ static uint64_t n_local_amps(const psum_handle_s* h) { return 1ull << h->n_loc; 
 
 static void free_device(psum_handle_s* h) {
   if (h->arena) cudaFree(h->arena);
+  if (h->arena_h) cudaFree(h->arena_h);
+  h->arena_h = nullptr;
+  h->dparts_h.clear();
+  h->parts_h.clear();
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_scalar) cudaFree(h->d_scalar);
   if (h->h_scalar) cudaFreeHost(h->h_scalar);
@@ -172,29 +186,19 @@ static T* arena_put(char* base, size_t& off, const std::vector<T>& v, std::vecto
   return p;
 }
 
-static int upload(psum_handle_s* h) {
-  if (h->uploaded) return PSUM_OK;
-  if (!h->planned) PS_TRY(plan(h));
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail(PSUM_ERR_CUDA, "no CUDA device available (%s); libpsum has no CPU fallback",
-                cudaGetErrorString(e));
-  CUDA_TRY(cudaGetDevice(&h->device));
-  CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
-  // two-phase arena: first size, then fill
+// Uploads one plan (vector of parts) into its own device arena.
+static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, void** arena,
+                       std::vector<DevPart>* dparts, size_t* partials_out) {
   std::vector<char> host;
   size_t off = 0;
-  // phase 1 to compute offsets with a null base
-  h->dparts.clear();
   size_t max_partials = 0;
   for (int phase = 0; phase < 2; ++phase) {
-    char* base = (char*)h->arena;
+    char* base = (char*)*arena;
     off = 0;
     host.clear();
-    h->dparts.clear();
+    dparts->clear();
     max_partials = 0;
-    for (const PartHost& P : h->parts) {
+    for (const PartHost& P : parts) {
       DevPart D;
       D.g = P.g;
       D.sgroups = arena_put(base, off, P.sgroups, host);
@@ -219,6 +223,8 @@ static int upload(psum_handle_s* h) {
         dp.params.L = ph.L;
         dp.params.n_nonfree = h->n_loc - ph.L;
         dp.params.ntiles = 1ull << (h->n_loc - ph.L);
+        dp.params.tile_begin = 0;
+        dp.params.tile_end = dp.params.ntiles;
         int nj = 0;
         for (int b = 0; b < h->n_loc; ++b)
           if (!(ph.free_mask >> b & 1ull)) dp.params.nbit[nj++] = (uint8_t)b;
@@ -230,6 +236,7 @@ static int upload(psum_handle_s* h) {
           dp.params.roff[r] = 16ull * o;
         }
         dp.has_im = ph.has_im;
+        dp.hi_bit = ph.hi_bit;
         dp.smem = pass_smem_bytes(ph.L);
         dp.threads = ph.L >= 13 ? 512 : 256;   // 2^13 tiles: one 512-thread CTA per SM
         int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
@@ -239,16 +246,32 @@ static int upload(psum_handle_s* h) {
       }
       partials = std::max(partials, pass_partials);
       max_partials += partials;
-      h->dparts.push_back(std::move(D));
+      dparts->push_back(std::move(D));
     }
     if (phase == 0) {
       size_t bytes = std::max<size_t>(off, 256);
-      CUDA_TRY(cudaMalloc(&h->arena, bytes));
+      CUDA_TRY(cudaMalloc(arena, bytes));
     } else if (off) {
-      CUDA_TRY(cudaMemcpy(h->arena, host.data(), off, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(*arena, host.data(), off, cudaMemcpyHostToDevice));
     }
   }
-  h->partial_cap = std::max<size_t>(max_partials, 4096) * 2 + 64 * 4096;
+  *partials_out = max_partials;
+  return PSUM_OK;
+}
+
+static int upload(psum_handle_s* h) {
+  if (h->uploaded) return PSUM_OK;
+  if (!h->planned) PS_TRY(plan(h));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PSUM_ERR_CUDA, "no CUDA device available (%s); libpsum has no CPU fallback",
+                cudaGetErrorString(e));
+  CUDA_TRY(cudaGetDevice(&h->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  size_t max_partials = 0;
+  PS_TRY(upload_plan(h, h->parts, &h->arena, &h->dparts, &max_partials));
+  h->partial_cap = std::max<size_t>(max_partials, 4096) * 2 + 128 * 4096;
   CUDA_TRY(cudaMalloc(&h->d_partial, h->partial_cap * sizeof(double2)));
   CUDA_TRY(cudaMalloc(&h->d_scalar, 256 * sizeof(double2)));
   CUDA_TRY(cudaMallocHost(&h->h_scalar, 256 * sizeof(double2)));
@@ -307,6 +330,10 @@ extern "C" int psum_destroy(psum_handle_t h) {
   free_device(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_free) cudaEventDestroy(h->ev_free);
+  for (auto& ev : h->ev_chunk)
+    if (ev) cudaEventDestroy(ev);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_recv[i]) cudaEventDestroy(h->ev_recv[i]);
@@ -334,6 +361,9 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "plan_tries") {
     if (value < 1 || value > 4096) return fail(PSUM_ERR_INVALID, "plan_tries must be 1..4096");
     h->opt.plan_tries = (int)value;
+  } else if (k == "late_bits") {
+    if (value < 0 || value > 8) return fail(PSUM_ERR_INVALID, "late_bits must be 0..8");
+    h->opt.late_bits = (int)value;
   } else if (k == "herm_pairing") {
     h->herm_pairing = value ? 1 : 0;
     return PSUM_OK;
@@ -409,14 +439,22 @@ extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask
 // Runs one part.  With a y buffer every pass accumulates into y and only the launch flagged
 // `last` reduces <bra|y> over the FINAL y; without y each pass appends the partials of its own
 // contribution at d_partial[*pcount...].
+// pass_lo/pass_hi and chunk/nchunks restrict the launch to a pass range and to the tiles of one
+// 2^(n_loc - log2 nchunks)-amplitude chunk (only valid for passes whose hi_bit lies inside a chunk).
 static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, const double2* bra,
                     double2* y, int accumulate, bool want_expect, bool last_part, size_t* pcount,
-                    cudaStream_t st) {
+                    cudaStream_t st, size_t pass_lo = 0, size_t pass_hi = (size_t)-1, uint64_t chunk = 0,
+                    uint64_t nchunks = 1) {
   const bool bra_is_src = (bra == src) || bra == nullptr;
   if (!D.passes.empty()) {
-    for (size_t pi = 0; pi < D.passes.size(); ++pi) {
+    for (size_t pi = pass_lo; pi < std::min(pass_hi, D.passes.size()); ++pi) {
       const DevPass& dp = D.passes[pi];
       PassParams pp = dp.params;
+      if (nchunks > 1) {
+        const uint64_t per = pp.ntiles / nchunks;
+        pp.tile_begin = chunk * per;
+        pp.tile_end = pp.tile_begin + per;
+      }
       pp.accumulate = (accumulate || pi > 0) ? 1 : 0;
       const bool last = last_part && (pi + 1 == D.passes.size());
       const bool ex = want_expect && (y ? last : true);
@@ -505,6 +543,69 @@ extern "C" int psum_apply(psum_handle_t h, const void* psi_dev, void* y_dev, dou
 extern "C" int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], psum_stream_t stream) {
   if (!h || !out) return fail(PSUM_ERR_INVALID, "null argument");
   return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, nullptr, out, (cudaStream_t)stream);
+}
+
+// <psi|H|psi> for a state that lives in HOST memory: the H2D copy is cut into 2^late_bits chunks
+// on a copy stream and every "early" pass (hi_bit inside a chunk) runs chunk by chunk as the data
+// arrives; only the passes that combine different chunks wait for the whole state.
+extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi_dev, double out[2],
+                                psum_stream_t stream) {
+  if (!h || !psi_host || !psi_dev || !out) return fail(PSUM_ERR_INVALID, "null argument");
+  if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle is sharded");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if ((uintptr_t)psi_dev & 15u) return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
+  PS_TRY(upload(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t N = n_local_amps(h);
+  const size_t bytes = N * sizeof(double2);
+  int late = 0;
+  if (h->n_loc >= 20 && h->opt.kernel != 1) late = std::min(4, h->n_loc - std::max(11, std::min(h->opt.tile_bits, kMaxTileBits)));
+  if (late <= 0) {  // small state: one copy, then the ordinary expectation
+    CUDA_TRY(cudaMemcpyAsync(psi_dev, psi_host, bytes, cudaMemcpyHostToDevice, st));
+    return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, nullptr, out, st);
+  }
+  if (h->parts_h.empty() || h->late_bits_h != late) {
+    PlanOptions o = h->opt;
+    o.late_bits = late;
+    h->parts_h = build_parts(h->terms, h->n, 0, 0, o);
+    if (h->arena_h) cudaFree(h->arena_h);
+    h->arena_h = nullptr;
+    size_t need = 0;
+    PS_TRY(upload_plan(h, h->parts_h, &h->arena_h, &h->dparts_h, &need));
+    h->late_bits_h = late;
+  }
+  if (!h->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+  }
+  const uint64_t nchunks = 1ull << late;
+  for (uint64_t k = 0; k < nchunks; ++k)
+    if (!h->ev_chunk[k]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+  // the copy may only start once earlier work on `stream` has released psi_dev
+  CUDA_TRY(cudaEventRecord(h->ev_free, st));
+  CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
+  const size_t cbytes = bytes >> late;
+  for (uint64_t k = 0; k < nchunks; ++k) {
+    CUDA_TRY(cudaMemcpyAsync((char*)psi_dev + k * cbytes, (const char*)psi_host + k * cbytes, cbytes,
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
+  }
+  if (h->dparts_h.size() != 1) return fail(PSUM_ERR_INVALID, "unexpected plan shape");
+  const DevPart& D = h->dparts_h[0];
+  const int cbits = h->n_loc - late;
+  size_t n_early = 0;  // early passes come first in the plan (stage 1 of choose_passes)
+  while (n_early < D.passes.size() && D.passes[n_early].hi_bit < cbits) ++n_early;
+  const double2* psi = (const double2*)psi_dev;
+  size_t pcount = 0;
+  for (uint64_t k = 0; k < nchunks; ++k) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
+    if (n_early) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, 0, n_early, k, nchunks));
+  }
+  if (n_early < D.passes.size())
+    PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, n_early, D.passes.size()));
+  k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
+  CUDA_TRY(cudaGetLastError());
+  return fetch_scalars(h, 1, out, st);
 }
 
 extern "C" int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, double out[2],

@@ -40,6 +40,7 @@ struct PassParams {
   int n_nonfree;
   int accumulate;
   uint64_t ntiles;
+  uint64_t tile_begin, tile_end;  // tile range of this launch (whole pass: 0 .. ntiles)
   uint64_t roff[8];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
   uint8_t fbit[16];  // qubit of tile bit j (0..4 lane, 5..7 register, 8.. warp/round)
   uint8_t nbit[64];  // positions of the non-free local bits, ascending
@@ -196,7 +197,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     }
   };
 
-  for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
+  for (uint64_t tile_id = P.tile_begin + blockIdx.x; tile_id < P.tile_end; tile_id += gridDim.x) {
     uint64_t base = 0;
     for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
 

@@ -88,6 +88,7 @@ struct PassHost {
   uint64_t free_mask = 0;      // over local qubits
   uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..7 register bits, 8.. warp/round
   bool has_im = false;         // any imaginary component pattern in this pass
+  int hi_bit = 0;              // highest local qubit the pass combines (free set or any member x-mask)
   int64_t n_flat = 0;          // groups whose D is the same for the 8 register amplitudes
   int64_t n_kind_a = 0;        // of those: local, <= 2 patterns (fast loop)
   std::vector<GroupRec> groups;
@@ -122,7 +123,8 @@ struct PlanOptions {
   int tile_bits = 12;
   int low_bits = 4;
   int min_cover = 3;
-  int plan_tries = 8;   // randomised greedy restarts of the pass planner; the cheapest plan wins
+  int plan_tries = 8;
+  int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)  // randomised greedy restarts of the pass planner; the cheapest plan wins
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
 };
 
@@ -172,7 +174,7 @@ struct PassChoice {
 };
 
 inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks, int n_loc, int L,
-                                             int c, int min_cover, uint64_t seed = 0) {
+                                             int c, int min_cover, uint64_t seed = 0, int late_bits = 0) {
   std::vector<PassChoice> passes;
   uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
   auto noise = [&]() {  // seed 0 -> deterministic greedy; otherwise scores are jittered by <= 40 %
@@ -186,62 +188,81 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
   c = std::min(c, L);
   const uint64_t low = low_mask(c);
   const uint64_t all = low_mask(n_loc);
-  std::vector<int> uncovered, remote;
+  // "late" qubits: the top late_bits local qubits.  Stage 1 plans the groups that do not touch
+  // them with free sets that avoid them, so those passes only ever combine amplitudes of one
+  // 2^(n_loc - late_bits) chunk -- they can run chunk by chunk while the state is still arriving
+  // from the host (psum_expect_host).  Stage 2 plans everything else.
+  late_bits = std::max(0, std::min(late_bits, n_loc - L));
+  const uint64_t late = all & ~low_mask(n_loc - late_bits);
+  std::vector<int> remote, stage1, stage2;
   for (int i = 0; i < (int)masks.size(); ++i) {
-    if (popc64(masks[i] & ~low) <= L - c) uncovered.push_back(i);
-    else remote.push_back(i);
+    if (popc64(masks[i] & ~low) > L - c) remote.push_back(i);
+    else if (masks[i] & late) stage2.push_back(i);
+    else stage1.push_back(i);
   }
   auto fill_mask = [&](uint64_t S) {  // pad with the lowest unused bits up to L bits
     for (int b = 0; b < n_loc && popc64(S) < L; ++b) S |= (1ull << b);
     return S;
   };
-  while (!uncovered.empty()) {
-    uint64_t S = low;
-    int remaining = L - c;
-    while (remaining > 0) {
-      double score[64];
-      for (int b = 0; b < 64; ++b) score[b] = 0.0;
-      bool any = false;
-      for (int i : uncovered) {
-        uint64_t need = masks[i] & ~S;
-        int nn = popc64(need);
-        if (nn == 0 || nn > remaining) continue;
-        any = true;
-        double w = 1.0 / (double)(nn * nn);
-        for (uint64_t m = need; m; m &= m - 1) score[__builtin_ctzll(m)] += w;
+  auto run_stage = [&](std::vector<int> uncovered, uint64_t allowed, std::vector<int>& leftover) {
+    while (!uncovered.empty()) {
+      uint64_t S = low;
+      int remaining = L - c;
+      while (remaining > 0) {
+        double score[64];
+        for (int b = 0; b < 64; ++b) score[b] = 0.0;
+        bool any = false;
+        for (int i : uncovered) {
+          uint64_t need = masks[i] & ~S;
+          int nn = popc64(need);
+          if (nn == 0 || nn > remaining || (need & ~allowed)) continue;
+          any = true;
+          double w = 1.0 / (double)(nn * nn);
+          for (uint64_t m = need; m; m &= m - 1) score[__builtin_ctzll(m)] += w;
+        }
+        if (!any) break;
+        int best = -1;
+        for (int b = 0; b < n_loc; ++b) score[b] *= noise();
+        for (int b = 0; b < n_loc; ++b)
+          if (!(S >> b & 1ull) && (allowed >> b & 1ull) && (best < 0 || score[b] > score[best])) best = b;
+        if (best < 0 || score[best] <= 0.0) break;
+        S |= 1ull << best;
+        --remaining;
       }
-      if (!any) break;
-      int best = -1;
-      for (int b = 0; b < n_loc; ++b) score[b] *= noise();
-      for (int b = 0; b < n_loc; ++b)
-        if (!(S >> b & 1ull) && (best < 0 || score[b] > score[best])) best = b;
-      if (best < 0 || score[best] <= 0.0) break;
-      S |= 1ull << best;
-      --remaining;
+      S = fill_mask(S) & all;
+      PassChoice pc;
+      pc.free_mask = S;
+      std::vector<int> rest;
+      for (int i : uncovered) {
+        if ((masks[i] & ~S) == 0) pc.members.push_back(i);
+        else rest.push_back(i);
+      }
+      if ((int)pc.members.size() < min_cover && !passes.empty()) {
+        // not worth a pass of its own (a pass re-reads psi and read-modify-writes y)
+        for (int i : uncovered) leftover.push_back(i);
+        return;
+      }
+      passes.push_back(std::move(pc));
+      uncovered.swap(rest);
     }
-    S = fill_mask(S) & all;
-    PassChoice pc;
-    pc.free_mask = S;
-    std::vector<int> rest;
-    for (int i : uncovered) {
-      if ((masks[i] & ~S) == 0) pc.members.push_back(i);
-      else rest.push_back(i);
-    }
-    if ((int)pc.members.size() < min_cover && !passes.empty()) {
-      // not worth a pass of its own (a pass re-reads psi and read-modify-writes y)
-      for (int i : uncovered) remote.push_back(i);
-      uncovered.clear();
-      break;
-    }
-    passes.push_back(std::move(pc));
-    uncovered.swap(rest);
+  };
+  if (late) {
+    std::vector<int> left1;
+    run_stage(stage1, all & ~late, left1);
+    for (int i : left1) stage2.push_back(i);
+  } else {
+    for (int i : stage1) stage2.push_back(i);
+    std::sort(stage2.begin(), stage2.end());
   }
+  run_stage(stage2, all, remote);
   if (passes.empty()) {
     PassChoice pc;
     pc.free_mask = fill_mask(low) & all;
     passes.push_back(pc);
   }
-  for (int i : remote) passes[0].members.push_back(i);
+  // groups no pass serves read their partners from global memory; they ride on the LAST pass so
+  // that the earlier (possibly chunk-local) passes stay chunk-local
+  for (int i : remote) passes.back().members.push_back(i);
   return passes;
 }
 
@@ -300,6 +321,11 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
   struct PatTmp { int cls; uint32_t zt; std::vector<int> terms; };
   struct SubGroup { GroupRec G; std::vector<PatTmp> pats; bool kind_a; int slot_of[2]; };
   std::vector<SubGroup> subs;
+  {
+    uint64_t u = S;
+    for (int mi : pc.members) u |= masks[mi];
+    P.hi_bit = u ? 63 - __builtin_clzll(u) : 0;
+  }
   for (int mi : pc.members) {
     const uint64_t xl = masks[mi];
     const bool remote = (xl & ~S) != 0;
@@ -498,7 +524,7 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
       std::vector<PassChoice> pcs;
       long best_cost = -1;
       for (int t = 0; t < std::max(1, opt.plan_tries); ++t) {
-        std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t);
+        std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t, opt.late_bits);
         long n_remote = 0;
         for (auto& pc : cand)
           for (int mi : pc.members)

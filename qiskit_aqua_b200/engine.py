@@ -146,6 +146,34 @@ class PauliSumEngine:
         check(lib().psum_expect(self._h, C.c_void_p(psi.data_ptr()), ex, _stream_ptr()))
         return complex(ex[0], ex[1])
 
+    def expect_host(self, psi_host, scratch=None):
+        """<psi|H|psi> for a HOST state (numpy array or CPU torch tensor, ideally pinned): the H2D
+        copy is pipelined with the chunk-local passes (psum_expect_host).  `scratch` is an optional
+        complex128 CUDA tensor of 2^n amplitudes that receives the copy."""
+        if not torch.cuda.is_available():
+            raise PsumError(_lib.ERR_CUDA, 'no CUDA device available; qiskit_aqua_b200 has no CPU fallback')
+        if isinstance(psi_host, torch.Tensor):
+            t = psi_host
+            if t.is_cuda:
+                return self.expect(t)
+            if t.dtype != torch.complex128 or not t.is_contiguous():
+                t = t.to(torch.complex128).contiguous()
+            host_ptr, keep = t.data_ptr(), t
+            n = t.numel()
+        else:
+            a = np.ascontiguousarray(np.asarray(psi_host, dtype=np.complex128)).reshape(-1)
+            host_ptr, keep = a.ctypes.data, a
+            n = a.size
+        if n != self.n_local_amps:
+            raise ValueError('state vector has %d amplitudes, expected %d' % (n, self.n_local_amps))
+        if scratch is None:
+            scratch = torch.empty(n, dtype=torch.complex128, device='cuda')
+        ex = (C.c_double * 2)()
+        check(lib().psum_expect_host(self._h, C.c_void_p(host_ptr), C.c_void_p(scratch.data_ptr()), ex,
+                                     _stream_ptr()))
+        del keep
+        return complex(ex[0], ex[1])
+
     def bra_apply(self, phi, psi):
         phi = as_device_state(phi, self.n_local_amps)
         psi = as_device_state(psi, self.n_local_amps)

@@ -353,6 +353,8 @@ class WeightedPauliOperator(LegacyBaseOperator):
         ``quantum_state`` may be a numpy array (copied to the device) or a complex128 CUDA tensor."""
         if self.is_empty():
             raise AquaError('Operator is empty, check the operator.')
+        if not getattr(quantum_state, 'is_cuda', False) and self.engine.world == 1:
+            return self.engine.expect_host(quantum_state), 0.0      # H2D pipelined with the passes
         psi = as_device_state(quantum_state, 1 << self.num_qubits)
         return self.engine.expect(psi), 0.0
 

@@ -193,3 +193,23 @@ def test_full_size_sampled_rows_and_properties(n):
     # linearity: H(2 psi) = 2 H psi  -> energy scales by 4
     psi *= 2.0
     assert abs(eng.expect(psi) - 4 * ex) <= RTOL * abs(4 * ex)
+
+
+@pytest.mark.parametrize('n,kind', [(12, 'numpy'), (20, 'numpy'), (21, 'pinned'), (22, 'complex')])
+def test_expect_host_pipelined(n, kind):
+    """psum_expect_host: chunked H2D overlapped with the chunk-local passes must give the same
+    <psi|H|psi> as the resident-state kernels and the oracle."""
+    if kind == 'complex':
+        _, x, z, y, c = W.random_weighted_paulis(n, 300, 3, seed=n)
+        c = c * (1.0 + 0.25j)                      # non-Hermitian: generic (unpaired) kernels
+    else:
+        _, x, z, y, c = W.two_local_random(n, 400, seed=n)
+    eng = PauliSumEngine(n, x, z, y, c)
+    psi = _state(n, n)
+    ref = co.expect(n, x, z, y, c, psi)
+    host = torch.from_numpy(psi).pin_memory() if kind == 'pinned' else psi
+    got = eng.expect_host(host)
+    assert abs(got - ref) <= RTOL * max(abs(ref), 1e-3)
+    assert abs(eng.expect(psi) - ref) <= RTOL * max(abs(ref), 1e-3)
+    got2 = eng.expect_host(host)                   # second call reuses the plan and the streams
+    assert abs(got2 - got) <= 1e-13 * max(abs(got), 1e-3)
