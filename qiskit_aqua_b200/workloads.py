@@ -97,3 +97,23 @@ def random_dense_paulis(n, n_terms, seed, complex_coeffs=False):
         if (x, z) not in terms:
             terms[(x, z)] = c
     return _finish(n, terms)
+
+
+def molecular_style(n=14, n_quads=170, seed=14):
+    """C3: synthetic molecular-style Hamiltonian: FermionicOperator with a seeded random symmetric
+    h1 and a sparse random h2 (chemists' index convention of the class, symmetrised so that H is
+    Hermitian), Jordan-Wigner mapped (reference qiskit/chemistry/fermionic_operator.py:344-474).
+    Returns (n, x, z, ypow, coeff) and the realised number of Pauli terms is len(x)."""
+    from .applications import FermionicOperator
+    rng = np.random.default_rng(seed)
+    h1 = rng.standard_normal((n, n))
+    h1 = 0.5 * (h1 + h1.T)
+    h2 = np.zeros((n, n, n, n))
+    for _ in range(n_quads):
+        i, j, k, m = (int(v) for v in rng.integers(0, n, size=4))
+        v = 0.5 * rng.standard_normal()
+        for a, b, c, d in ((i, j, k, m), (j, i, m, k), (k, m, i, j), (m, k, j, i)):
+            h2[a, b, c, d] += v
+    op = FermionicOperator(h1, h2).mapping('jordan_wigner')
+    terms = {(p.x_mask, p.z_mask): complex(w) for w, p in op.paulis}
+    return _finish(n, terms)
