@@ -220,7 +220,7 @@ def main():
         nrm2 = t.item()
         if info['n_global_parts'] > 0:
             free_b, _ = torch.cuda.mem_get_info()
-            nbuf = 2 if free_b > 3.2 * 16 * N_loc else 1
+            nbuf = int(max(1, min(info['n_global_parts'], (free_b - 2.5 * 16 * N_loc) // (16 * N_loc))))
             recv = torch.empty(nbuf * N_loc, dtype=torch.complex128, device='cuda')
     vec_scale(psi, 1.0 / np.sqrt(nrm2))
 

@@ -157,8 +157,8 @@ int psum_shard_terms(psum_handle_t h, int g, int64_t cap, uint64_t* x_local, uin
                      double* coeff_re_im, int64_t* n_out);
 /* Sharded H.psi with the NCCL amplitude exchange inside (needs psum_shard_init with an id):
  * recv_dev is a caller-provided exchange buffer of recv_amps >= N_loc amplitudes (may be NULL
- * when no term has a global x-part); with >= 2 N_loc the exchange of part g+1 overlaps the
- * passes over part g.  y_dev may be NULL (expectation only).  expect_out (may be NULL) receives
+ * when no term has a global x-part); it is used as a ring of floor(recv_amps / N_loc) <= 8
+ * shard buffers, so that many exchanges are in flight ahead of the part being computed.  y_dev may be NULL (expectation only).  expect_out (may be NULL) receives
  * the all-reduced <psi|H|psi>. */
 int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
                        uint64_t recv_amps, double* expect_out, psum_stream_t stream);

@@ -141,7 +141,7 @@ struct psum_handle_s {
   // sharding
   nccl_comm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_recv[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  cudaEvent_t ev_ready = nullptr, ev_recv[8] = {nullptr}, ev_used[8] = {nullptr};
 };
 
 static uint64_t n_local_amps(const psum_handle_s* h) { return 1ull << h->n_loc; }
@@ -335,7 +335,7 @@ extern "C" int psum_destroy(psum_handle_t h) {
   for (auto& ev : h->ev_chunk)
     if (ev) cudaEventDestroy(ev);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (h->ev_recv[i]) cudaEventDestroy(h->ev_recv[i]);
     if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
   }
@@ -831,7 +831,7 @@ extern "C" int psum_shard_init(psum_handle_t h, int rank, int world, const void*
     NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, id, rank));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 8; ++i) {
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_recv[i], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
     }
@@ -923,15 +923,15 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
     if (!h->comm) return fail(PSUM_ERR_NCCL, "terms with global x-parts need a communicator");
     if (!recv_dev || recv_amps < N) return fail(PSUM_ERR_INVALID, "recv_dev must hold one shard");
   }
-  const int nbuf = (recv_amps >= 2 * N) ? 2 : 1;
+  // ring of receive buffers: up to nbuf exchanges are in flight ahead of the part being computed,
+  // so with enough buffers every exchange hides behind the (long) local part
+  const int nbuf = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, recv_amps / std::max<uint64_t>(N, 1)));
   size_t pcount = 0;
   bool wrote_y = false;
   if (any_remote) {
     CUDA_TRY(cudaEventRecord(h->ev_ready, st));
     CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
   }
-  // local part first (overlaps the first exchange)
-  int slot = 0;
   std::vector<const DevPart*> remote;
   for (auto& D : h->dparts)
     if (D.g != 0) remote.push_back(&D);
@@ -946,8 +946,10 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
     CUDA_TRY(cudaEventRecord(h->ev_recv[s], h->comm_stream));
     return PSUM_OK;
   };
-  std::vector<bool> used_once(2, false);
-  if (!remote.empty()) PS_TRY(post_exchange(remote[0], 0, false));
+  size_t posted = 0;
+  for (; posted < remote.size() && posted < (size_t)nbuf; ++posted)
+    PS_TRY(post_exchange(remote[posted], (int)(posted % nbuf), false));
+  // local part (overlaps the exchanges posted above)
   for (auto& D : h->dparts)
     if (D.g == 0) {
       PS_TRY(run_part(h, D, psi, psi, y, 0, expect_out != nullptr, remote.empty(), &pcount, st));
@@ -955,18 +957,15 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
     }
   if (!wrote_y && y) CUDA_TRY(cudaMemsetAsync(y, 0, N * sizeof(double2), st));
   for (size_t r = 0; r < remote.size(); ++r) {
-    slot = (int)(r % nbuf);
-    // prefetch the next exchange into the other buffer
-    if (nbuf == 2 && r + 1 < remote.size()) {
-      int ns = (int)((r + 1) % 2);
-      PS_TRY(post_exchange(remote[r + 1], ns, used_once[ns]));
-    }
+    const int slot = (int)(r % nbuf);
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_recv[slot], 0));
     const double2* buf = (const double2*)recv_dev + (uint64_t)slot * N;
     PS_TRY(run_part(h, *remote[r], buf, psi, y, 1, expect_out != nullptr, r + 1 == remote.size(), &pcount, st));
     CUDA_TRY(cudaEventRecord(h->ev_used[slot], st));
-    used_once[slot] = true;
-    if (nbuf == 1 && r + 1 < remote.size()) PS_TRY(post_exchange(remote[r + 1], 0, true));
+    if (posted < remote.size()) {  // refill the slot that was just consumed
+      PS_TRY(post_exchange(remote[posted], slot, true));
+      ++posted;
+    }
   }
   if (expect_out) {
     k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);

@@ -33,8 +33,8 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         eng.shard(rank, world, uid[0])
         psi = fill_state(N_loc, seed=11, first_index=rank * N_loc)
-        recv = torch.empty(2 * N_loc, dtype=torch.complex128, device='cuda')
-        for rcv in (recv, recv[:N_loc]):
+        recv = torch.empty(max(2, world - 1) * N_loc, dtype=torch.complex128, device='cuda')
+        for rcv in (recv, recv[:2 * N_loc], recv[:N_loc]):   # ring of world-1, 2 and 1 shard buffers
             yv, ex = eng.apply_sharded(psi, recv=rcv, want_expect=True)
             _, ex2 = eng.apply_sharded(psi, recv=rcv, want_expect=True, store=False)
             gathered = [torch.empty_like(yv) for _ in range(world)]
