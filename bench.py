@@ -220,7 +220,9 @@ def main():
         nrm2 = t.item()
         if info['n_global_parts'] > 0:
             free_b, _ = torch.cuda.mem_get_info()
-            nbuf = int(max(1, min(info['n_global_parts'], (free_b - 2.5 * 16 * N_loc) // (16 * N_loc))))
+            # two exchange buffers: more were measured to bring nothing (the exchanges already hide
+            # behind the local part) and only raise the memory footprint
+            nbuf = 2 if free_b > 3.2 * 16 * N_loc else 1
             recv = torch.empty(nbuf * N_loc, dtype=torch.complex128, device='cuda')
     vec_scale(psi, 1.0 / np.sqrt(nrm2))
 
