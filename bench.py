@@ -311,11 +311,18 @@ def main():
             traffic = json.load(open(tpath)).get('dram_bytes_per_step')
         except Exception:
             traffic = None
+    # secondary, for context: what the DRAM and the shared-memory pipe actually see
+    dram_gbs = (traffic / (ms_step * 1e-3) / 1e9) if traffic else None
+    sm_mhz = 1965.0
+    smem_floor_ms = info['n_group_records'] * float(N_loc) * 16.0 / (148 * 128.0 * sm_mhz * 1e6) * 1e3
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'dram_achieved': dram_gbs, 'dram_frac': (dram_gbs / peak) if dram_gbs else None,
+                'smem_floor_ms': smem_floor_ms, 'smem_floor_frac': smem_floor_ms / ms_step,
                 'traffic': traffic, 'peak_source': peak_src, 'kernel': 'psum::k_pass (x%d launches per step)' % info['n_passes'],
                 'algorithmic_bytes_per_step': b_alg,
                 'note': 'B_alg = 16*N_loc*(G_x+1) (SURVEY 8d) counts one partner read per x-group; k_pass serves '
-                        'in-tile groups from shared memory, so DRAM traffic is far below B_alg and frac may exceed 1'}
+                        'in-tile groups from shared memory, so DRAM traffic is far below B_alg and frac exceeds 1; '
+                        'dram_* = ncu DRAM bytes / time, smem_floor = 16 B per (group record, amplitude) at 128 B/clk/SM'}
     launches = (info['n_passes'] + 1) * args.steps
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
