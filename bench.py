@@ -118,6 +118,7 @@ class ClockSampler:
 def cpu_sample(n_total, x, z, y, c, psi_host, budget_s=12.0, rows_per_call=1 << 18):
     """Times the oracle C matvec on successive row blocks of the same operator until budget_s."""
     from oracle import c_oracle as co
+    co.use_all_cores()
     T = len(x)
     done_rows, t_acc = 0, 0.0
     co.apply(n_total, x, z, y, c, psi_host, 0, 1 << 12)          # warm the threads
@@ -140,6 +141,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import c_oracle as co
+    co.use_all_cores()                  # torchrun sets OMP_NUM_THREADS=1 for its workers
     n_loc = args.qubits or 30
     n_total = n_loc + (args.gpus.bit_length() - 1)
     n_cpu = min(n_total, 30)           # host RAM bound for the state the CPU streams over

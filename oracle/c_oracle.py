@@ -29,6 +29,7 @@ def lib():
             build()
         _lib = C.CDLL(LIB)
         _lib.psum_oracle_threads.restype = C.c_int
+        _lib.psum_oracle_set_threads.argtypes = [C.c_int]
         _lib.psum_oracle_state.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, _dp]
         _lib.psum_oracle_apply.argtypes = [C.c_int, C.c_int64, _u64p, _u64p, _u8p, _dp, _dp, _dp,
                                            C.c_uint64, C.c_uint64]
@@ -52,6 +53,13 @@ def _terms(x, z, ypow, coeff):
 
 def threads():
     return lib().psum_oracle_threads()
+
+
+def use_all_cores():
+    """OpenMP thread count := cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    lib().psum_oracle_set_threads(n)
+    return threads()
 
 
 def counter_state(seed, first, count):

@@ -31,6 +31,15 @@ static inline double counter_uniform(uint64_t seed, uint64_t ctr) {
   return (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must still use every host core */
+void psum_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int psum_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
