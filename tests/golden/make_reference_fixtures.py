@@ -1,0 +1,149 @@
+"""Runs the REFERENCE'S OWN code for the hot path in the build container and records its outputs
+as golden fixtures (tests/golden/reference_run.json).
+
+    python tests/golden/make_reference_fixtures.py        (needs /root/reference; CPU only)
+
+qiskit-terra is absent, so tests/golden/terra_stub.py supplies a restated `Pauli` and dummies for
+everything else; only the reference files on the path are executed for real:
+  qiskit/aqua/operators/legacy/{weighted_pauli_operator,op_converter,matrix_operator,base_operator,common}.py
+  qiskit/aqua/{aqua_error,aqua_globals,missing_optional_library_error}.py
+  qiskit/optimization/applications/ising/{max_cut,common}.py
+  qiskit/chemistry/fermionic_operator.py
+The package __init__ files of the reference are NOT executed (they import the whole of terra);
+synthetic parent packages give the relative imports something to hang on.
+"""
+import itertools
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import terra_stub  # noqa: E402
+
+REF = '/root/reference/qiskit'
+
+
+def load_reference():
+    terra_stub.install()
+    import qiskit  # noqa: F401  (stub package)
+
+    import importlib
+
+    def synth(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        m.__package__ = name
+        sys.modules[name] = m
+        parent, _, leaf = name.rpartition('.')
+        setattr(sys.modules[parent], leaf, m)
+        return m
+
+    aqua = synth('qiskit.aqua', REF + '/aqua')
+    ae = importlib.import_module('qiskit.aqua.aqua_error')
+    ag = importlib.import_module('qiskit.aqua.aqua_globals')
+    mo = importlib.import_module('qiskit.aqua.missing_optional_library_error')
+    aqua.AquaError, aqua.aqua_globals, aqua.MissingOptionalLibraryError = ae.AquaError, ag.aqua_globals, mo.MissingOptionalLibraryError
+    ops = synth('qiskit.aqua.operators', REF + '/aqua/operators')
+    synth('qiskit.aqua.operators.legacy', REF + '/aqua/operators/legacy')
+    from qiskit.aqua.operators.legacy.weighted_pauli_operator import WeightedPauliOperator
+    from qiskit.aqua.operators.legacy.matrix_operator import MatrixOperator
+    from qiskit.aqua.operators.legacy import op_converter
+    ops.WeightedPauliOperator = WeightedPauliOperator
+    ops.StateFn = terra_stub.get_class('StateFn')
+    synth('qiskit.optimization', REF + '/optimization')
+    synth('qiskit.optimization.applications', REF + '/optimization/applications')
+    synth('qiskit.optimization.applications.ising', REF + '/optimization/applications/ising')
+    from qiskit.optimization.applications.ising import common, max_cut
+    chem = synth('qiskit.chemistry', REF + '/chemistry')
+    ce = importlib.import_module('qiskit.chemistry.qiskit_chemistry_error')
+    chem.QiskitChemistryError = ce.QiskitChemistryError
+    sys.modules.setdefault('retworkx', types.ModuleType('retworkx'))   # only bksf.py wants it; unused here
+    from qiskit.chemistry.fermionic_operator import FermionicOperator
+    return dict(WPO=WeightedPauliOperator, MatrixOperator=MatrixOperator, op_converter=op_converter,
+                common=common, max_cut=max_cut, FermionicOperator=FermionicOperator, aqua_globals=ag.aqua_globals,
+                AquaError=ae.AquaError)
+
+
+def cplx(v):
+    v = complex(v)
+    return [v.real, v.imag]
+
+
+def main():
+    R = load_reference()
+    WPO, Pauli = R['WPO'], terra_stub.Pauli
+    out = {'note': 'outputs of the reference code itself (terra Pauli stubbed); see make_reference_fixtures.py',
+           'operators': [], 'maxcut': [], 'fermionic': []}
+    rng = np.random.default_rng(2024)
+    for case in range(14):
+        n = int(rng.integers(1, 7))
+        T = int(rng.integers(1, 40))
+        labels = [''.join(rng.choice(list('IXYZ')) for _ in range(n)) for _ in range(T)]
+        if T > 3:                                    # force duplicates and an exact cancellation
+            labels[1] = labels[0]
+            labels[-1] = labels[2]
+        weights = (rng.standard_normal(T) + (1j * rng.standard_normal(T) if case % 3 == 0 else 0)).astype(complex)
+        if T > 3:
+            weights[-1] = -weights[2]
+        op = WPO(paulis=[[complex(w), Pauli(l)] for w, l in zip(weights, labels)])
+        psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        psi /= np.linalg.norm(psi)
+        rec = {'n': n, 'input_labels': labels, 'input_weights': [cplx(w) for w in weights],
+               'simplified': [[cplx(w), p.to_label()] for w, p in op.paulis],
+               'psi': [cplx(v) for v in psi]}
+        if not op.is_empty():
+            mean, std = op.evaluate_with_statevector(psi)
+            rec['evaluate_with_statevector'] = cplx(mean)
+            rec['std'] = std
+            mat = R['op_converter'].to_matrix_operator(op)
+            rec['matrix_operator_evaluate'] = cplx(mat.evaluate_with_statevector(psi)[0])
+            hpsi = mat._matrix.dot(psi)
+            rec['h_psi'] = [cplx(v) for v in hpsi]
+            rec['to_dict'] = op.to_dict()
+            rec['chop_0.5'] = [[cplx(w), p.to_label()] for w, p in op.chop(0.5, copy=True).paulis]
+        else:
+            try:
+                op.evaluate_with_statevector(psi)
+                rec['empty_raises'] = False
+            except R['AquaError']:
+                rec['empty_raises'] = True
+        out['operators'].append(rec)
+    # MaxCut generators (configs 1, G7)
+    for n, seed, p in ((4, 8123179999, 0.5), (6, 99, 0.5), (16, 17, 0.5)):
+        w = R['common'].random_graph(n, weight_range=10, edge_prob=p, negative_weight=True, seed=seed)
+        op, shift = R['max_cut'].get_operator(w)
+        out['maxcut'].append({'n': n, 'seed': seed, 'edge_prob': p, 'w': w.tolist(), 'shift': float(shift),
+                              'paulis': [[cplx(wt), pl.to_label()] for wt, pl in op.paulis]})
+    # Jordan-Wigner mapping (configs 3, G10): H2 integrals + a random sparse case
+    chem = json.load(open(os.path.join(HERE, 'chemistry_integrals.json')))['G10_h2_fcidump']
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import pauli_oracle as po
+    h1 = po.onee_to_spin(np.array(chem['mo_onee']))
+    h2 = po.twoe_to_spin(np.array(chem['mo_eri']))
+    cases = [('h2_fcidump', h1, h2)]
+    r2 = np.random.default_rng(7)
+    g1 = r2.standard_normal((5, 5))
+    g1 = g1 + g1.T
+    g2 = np.zeros((5,) * 4)
+    for _ in range(10):
+        i, j, k, m = r2.integers(0, 5, size=4)
+        g2[i, j, k, m] = r2.standard_normal()
+    cases.append(('random5', g1, g2))
+    for name, a, b in cases:
+        op = R['FermionicOperator'](a, b).mapping('jordan_wigner')
+        out['fermionic'].append({'name': name, 'h1': a.tolist(), 'h2_nonzero': [[int(v) for v in idx] + [float(b[idx])]
+                                                                               for idx in zip(*np.nonzero(b))],
+                                 'modes': int(a.shape[0]),
+                                 'paulis': [[cplx(w), p.to_label()] for w, p in op.paulis]})
+    path = os.path.join(HERE, 'reference_run.json')
+    with open(path, 'w') as f:
+        json.dump(out, f)
+    print('wrote', path, os.path.getsize(path), 'bytes;', len(out['operators']), 'operator cases')
+
+
+if __name__ == '__main__':
+    main()

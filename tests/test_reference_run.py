@@ -1,0 +1,101 @@
+"""Fixtures produced by running the REFERENCE'S OWN code in the build container
+(tests/golden/make_reference_fixtures.py -> tests/golden/reference_run.json: the real
+WeightedPauliOperator / op_converter / MatrixOperator / max_cut / common.random_graph /
+FermionicOperator modules of qiskit-aqua 0.10.0, with only terra's Pauli stubbed).
+CPU part: the oracle and the host-side shim must reproduce them.  GPU part: so must the kernels."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pauli_oracle as po
+from qiskit_aqua_b200 import FermionicOperator, Pauli, WeightedPauliOperator, max_cut, random_graph
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, 'golden', 'reference_run.json')) as _f:
+    REF = json.load(_f)
+
+
+def _c(pair):
+    return complex(pair[0], pair[1])
+
+
+@pytest.mark.parametrize('case', range(len(REF['operators'])))
+def test_container_semantics_and_expectation_vs_reference(case):
+    rec = REF['operators'][case]
+    n = rec['n']
+    weights = [_c(w) for w in rec['input_weights']]
+    labels = rec['input_labels']
+    ref_simpl = [(_c(w), lab) for w, lab in rec['simplified']]
+    # oracle
+    got = po.simplify(list(zip(weights, labels)))
+    assert [lab for _, lab in got] == [lab for _, lab in ref_simpl]
+    np.testing.assert_allclose([w for w, _ in got], [w for w, _ in ref_simpl], rtol=0, atol=1e-15)
+    # product shim
+    op = WeightedPauliOperator(paulis=[[w, Pauli(lab)] for w, lab in zip(weights, labels)])
+    assert [p.to_label() for _, p in op.paulis] == [lab for _, lab in ref_simpl]
+    np.testing.assert_allclose([complex(w) for w, _ in op.paulis], [w for w, _ in ref_simpl], rtol=0, atol=1e-15)
+    psi = np.array([_c(v) for v in rec['psi']])
+    if 'evaluate_with_statevector' not in rec:
+        assert rec['empty_raises'] and op.is_empty()
+        return
+    ref_e = _c(rec['evaluate_with_statevector'])
+    assert abs(po.ref_evaluate_with_statevector(got, psi)[0] - ref_e) < 1e-12
+    assert abs(_c(rec['matrix_operator_evaluate']) - ref_e) < 1e-12
+    x, z, y, c = po.pack_terms(got)
+    np.testing.assert_allclose(po.mf_apply(n, x, z, y, c, psi), [_c(v) for v in rec['h_psi']], rtol=0, atol=1e-12)
+    chopped = op.chop(0.5, copy=True)
+    assert [p.to_label() for _, p in chopped.paulis] == [lab for _, lab in rec['chop_0.5']]
+    np.testing.assert_allclose([complex(w) for w, _ in chopped.paulis], [_c(w) for w, _ in rec['chop_0.5']],
+                               rtol=0, atol=1e-15)
+    d = op.to_dict()
+    assert [e['label'] for e in d['paulis']] == [e['label'] for e in rec['to_dict']['paulis']]
+    for a, b in zip(d['paulis'], rec['to_dict']['paulis']):
+        assert abs(a['coeff']['real'] - b['coeff']['real']) < 1e-15
+        assert abs(a['coeff'].get('imag', 0.0) - b['coeff'].get('imag', 0.0)) < 1e-15
+
+
+def test_maxcut_generators_vs_reference():
+    for rec in REF['maxcut']:
+        w = random_graph(rec['n'], weight_range=10, edge_prob=rec['edge_prob'], negative_weight=True,
+                         seed=rec['seed'])
+        np.testing.assert_array_equal(w, np.array(rec['w']))
+        np.testing.assert_array_equal(po.random_graph(rec['n'], 10, rec['edge_prob'], True, seed=rec['seed']), w)
+        op, shift = max_cut.get_operator(w)
+        assert shift == rec['shift']
+        assert [(complex(a), p.to_label()) for a, p in op.paulis] == [(_c(a), lab) for a, lab in rec['paulis']]
+        terms, oshift = po.max_cut_operator(w)
+        assert oshift == rec['shift']
+        assert [(complex(a), lab) for a, lab in terms] == [(_c(a), lab) for a, lab in rec['paulis']]
+
+
+def test_jordan_wigner_vs_reference():
+    for rec in REF['fermionic']:
+        m = rec['modes']
+        h1 = np.array(rec['h1'])
+        h2 = np.zeros((m,) * 4)
+        for i, j, k, l, v in rec['h2_nonzero']:
+            h2[i, j, k, l] = v
+        ref = [(_c(w), lab) for w, lab in rec['paulis']]
+        for got in (po.jordan_wigner(h1, h2),
+                    [(complex(w), p.to_label()) for w, p in FermionicOperator(h1, h2).mapping('jordan_wigner').paulis]):
+            assert [lab for _, lab in got] == [lab for _, lab in ref]
+            np.testing.assert_allclose([w for w, _ in got], [w for w, _ in ref], rtol=0, atol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', range(len(REF['operators'])))
+def test_kernels_vs_reference_run(case):
+    pytest.importorskip('torch')
+    rec = REF['operators'][case]
+    if 'evaluate_with_statevector' not in rec:
+        pytest.skip('empty operator case')
+    op = WeightedPauliOperator(paulis=[[_c(w), Pauli(lab)] for w, lab in zip(rec['input_weights'], rec['input_labels'])])
+    psi = np.array([_c(v) for v in rec['psi']])
+    mean, std = op.evaluate_with_statevector(psi)
+    ref_e = _c(rec['evaluate_with_statevector'])
+    assert std == 0.0 and abs(mean - ref_e) <= 1e-10 * max(1.0, abs(ref_e))
+    y = op.engine.apply(psi).cpu().numpy()
+    ref_y = np.array([_c(v) for v in rec['h_psi']])
+    assert np.abs(y - ref_y).max() <= 1e-10 * max(1.0, np.abs(ref_y).max())
