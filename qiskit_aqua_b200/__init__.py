@@ -13,5 +13,5 @@ from .operators import (AquaError, ComposedOp, I, ListOp, MatrixExpectation, Ope
 from .algorithms import (EigensolverResult, MinimumEigensolverResult, NumPyEigensolver,  # noqa: F401,E402
                          NumPyMinimumEigensolver)
 from .applications import FermionicOperator, max_cut, random_graph, sample_most_likely  # noqa: F401,E402
-from .circuits import (CircuitStateFn, EfficientSU2, RealAmplitudes, StatevectorCircuit,  # noqa: F401,E402
+from .circuits import (VQE, CircuitStateFn, EfficientSU2, RealAmplitudes, StatevectorCircuit,  # noqa: F401,E402
                        energy_evaluation)

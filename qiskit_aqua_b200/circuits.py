@@ -173,3 +173,39 @@ def energy_evaluation(operator, ansatz, parameters):
         buf = ansatz.run(row, out=buf)
         out.append(eng.expect(buf).real)
     return out[0] if len(out) == 1 else np.array(out)
+
+
+class VQE:
+    """Thin caller around the device path (the optimiser loop itself is host-side scipy, as the
+    reference's is host-side Python): minimises energy_evaluation over the ansatz parameters.
+    Mirrors the result fields of reference algorithms/minimum_eigen_solvers/vqe.py:403-467
+    (eigenvalue, optimal_point, optimal_value, cost_function_evals, eigenstate)."""
+
+    def __init__(self, operator, var_form, optimizer='SLSQP', initial_point=None, maxiter=300, seed=0,
+                 callback=None):
+        self.operator, self.var_form = operator, var_form
+        self.optimizer, self.maxiter = optimizer, maxiter
+        self.initial_point = initial_point
+        self.seed = seed
+        self.callback = callback
+        self._evals = 0
+
+    def _cost(self, theta):
+        self._evals += 1
+        val = float(energy_evaluation(self.operator, self.var_form, theta))
+        if self.callback is not None:
+            self.callback(self._evals, theta, val, 0.0)
+        return val
+
+    def run(self):
+        from scipy.optimize import minimize
+        rng = np.random.default_rng(self.seed)
+        x0 = np.asarray(self.initial_point, dtype=float) if self.initial_point is not None \
+            else rng.uniform(-np.pi, np.pi, self.var_form.num_parameters)
+        self._evals = 0
+        res = minimize(self._cost, x0, method=self.optimizer, options={'maxiter': self.maxiter})
+        state = self.var_form.run(res.x)
+        return {'eigenvalue': complex(res.fun), 'optimal_value': float(res.fun), 'optimal_point': res.x,
+                'cost_function_evals': self._evals, 'eigenstate': state, 'optimizer_message': str(res.message)}
+
+    compute_minimum_eigenvalue = run

@@ -76,3 +76,14 @@ def test_ghz_and_ansatz_energy():
             assert abs(means[k] - ref_e) < 1e-12
         val = (~StateFn(op) @ CircuitStateFn(ansatz, theta[:ansatz.num_parameters])).eval()
         assert abs(val.real - means[0]) < 1e-12
+
+
+def test_vqe_h2_reaches_reference_energy():
+    # test/aqua/test_vqe.py:38-60: H2 qubit operator, RY-RZ ansatz, SLSQP -> -1.85727503
+    from qiskit_aqua_b200 import VQE
+    h2 = [(-1.052373245772859, 'II'), (0.39793742484318045, 'ZI'), (-0.39793742484318045, 'IZ'),
+          (-0.01128010425623538, 'ZZ'), (0.18093119978423156, 'XX')]
+    op = WeightedPauliOperator(paulis=[[w, Pauli(l)] for w, l in h2])
+    best = min(VQE(op, EfficientSU2(2, reps=2, entanglement='linear'), optimizer='SLSQP', seed=s).run()['optimal_value']
+               for s in range(3))
+    assert abs(best - (-1.85727503)) < 1e-5
