@@ -141,3 +141,38 @@ def test_c_oracle_matches_numpy_oracle():
     rows = np.array([0, 17, (1 << n) - 1], dtype=np.uint64)
     np.testing.assert_allclose(co.apply_rows_counter(x, z, y, c, 5, 1.0, rows),
                                po.mf_apply(n, x, z, y, c, s, rows), atol=1e-12 * np.abs(ref).max())
+
+
+def test_plan_up_to_64_qubits_and_sharded():
+    rng = np.random.default_rng(64)
+    for n in (40, 64):
+        T = 300
+        x = np.zeros(T, dtype=np.uint64)
+        z = np.zeros(T, dtype=np.uint64)
+        for k in range(T):
+            for q in rng.choice(n, size=3, replace=False):
+                p = rng.integers(0, 3)
+                if p < 2:
+                    x[k] |= np.uint64(1) << np.uint64(int(q))
+                if p > 0:
+                    z[k] |= np.uint64(1) << np.uint64(int(q))
+        y = np.array([bin(int(a) & int(b)).count('1') & 3 for a, b in zip(x, z)], dtype=np.uint8)
+        eng = PauliSumEngine(n, x, z, y, rng.standard_normal(T).astype(complex))
+        info = eng.info()
+        assert info['n_qubits'] == n and info['n_passes'] >= 1
+        assert sum(eng.pass_info(p)['n_groups'] for p in range(info['n_passes'])) == info['n_xgroups']
+        eng.shard(5, 8)
+        info = eng.info()
+        assert info['n_local_qubits'] == n - 3 and 1 <= info['n_global_parts'] <= 7
+
+
+def test_late_bits_keeps_early_passes_chunk_local():
+    n, x, z, y, c = W.ising_heisenberg(24, n_triples=2000, seed=3)
+    eng = PauliSumEngine(n, x, z, y, c, {'late_bits': 4})
+    info = eng.info()
+    masks = [eng.pass_info(p)['free_mask'] for p in range(info['n_passes'])]
+    early = [m for m in masks if m < (1 << 20)]
+    assert len(early) >= info['n_passes'] // 2            # most passes never touch the top 4 qubits
+    k = len(early)
+    assert all(m < (1 << 20) for m in masks[:k])           # and they come first in the plan
+    assert sum(eng.pass_info(p)['n_groups'] for p in range(info['n_passes'])) == info['n_xgroups']
