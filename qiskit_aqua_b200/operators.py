@@ -450,6 +450,43 @@ class _PauliSumMixin(OperatorBase):
     def to_legacy_op(self):
         return WeightedPauliOperator(paulis=[[w, p] for w, p in _terms_of(self)])
 
+    def _check_massive(self, method, matrix, num_qubits, massive):
+        """operator_base.py:618-648: refuse dense conversions above 16 qubits unless massive."""
+        if num_qubits > 16 and not massive:
+            dim = 2 ** num_qubits
+            if matrix:
+                obj_type = 'matrix'
+                dimensions = '{}x{}'.format(dim, dim)
+            else:
+                obj_type = 'vector'
+                dimensions = str(dim)
+            raise ValueError(
+                "'{}' will return an exponentially large {}, in this case '{}' elements. "
+                "Set aqua_globals.massive=True or the method argument massive=True "
+                "if you want to proceed.".format(method, obj_type, dimensions))
+
+    def to_matrix(self, massive=False):
+        """Dense matrix (primitive_ops/pauli_op.py:151-153, list_ops/list_op.py:306-318), produced
+        column by column with the matrix-free device kernel: column j = H e_j.  Meant for the small
+        operators the reference's tests inspect; the hot path never builds it."""
+        import torch
+        n = self.num_qubits
+        self._check_massive('to_matrix', True, n, massive)
+        N = 1 << n
+        eng = self._engine_for()
+        out = torch.empty((N, N), dtype=torch.complex128, device='cuda')      # row j holds column j
+        e = torch.zeros(N, dtype=torch.complex128, device='cuda')
+        for j in range(N):
+            e[j] = 1.0
+            eng.apply(e, out=out[j])
+            e[j] = 0.0
+        return out.t().contiguous().cpu().numpy()
+
+    def to_spmatrix(self):
+        """scipy CSR of the operator (pauli_op.py:164, list_op.py:320-329); small operators only."""
+        import scipy.sparse as sp
+        return sp.csr_matrix(self.to_matrix())
+
     def add(self, other):
         if other == 0:
             return self

@@ -148,3 +148,16 @@ def test_maxcut_g7_diagonal_branch():
     terms, _ = po.max_cut_operator(w)
     ref, _ = po.ref_solve(terms, k=3)
     np.testing.assert_allclose(np.real(res.eigenvalues), ref.real, atol=1e-12)
+
+
+def test_to_matrix_and_massive_guard():
+    # test_op_construction.py:158-162 ((X^Y).to_matrix() == kron(X, Y)) and operator_base.py:634-648
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    y = np.array([[0, -1j], [1j, 0]], dtype=complex)
+    np.testing.assert_allclose((X ^ Y).to_matrix(), np.kron(x, y), atol=1e-15)
+    h = 0.5 * (X ^ X ^ I) + (Z ^ I ^ Y) - 0.25j * (Y ^ Y ^ Z)
+    terms = [(w, p.to_label()) for w, p in h.to_legacy_op().paulis]
+    np.testing.assert_allclose(h.to_matrix(), po.ref_to_spmatrix(terms).toarray(), atol=1e-14)
+    np.testing.assert_allclose(h.to_spmatrix().toarray(), po.ref_to_spmatrix(terms).toarray(), atol=1e-14)
+    with pytest.raises(ValueError):
+        (X ^ 17).to_matrix()
