@@ -8,7 +8,7 @@ BASELINE.json.  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_basel
 Parity status: PINNED (i) by the reference's own golden vectors (SURVEY.md section 8c, G1..G13;
 ``tests/test_oracle_golden.py``) and (ii) by outputs of the reference's OWN code run in the build
 container -- WeightedPauliOperator / op_converter / MatrixOperator / max_cut / random_graph /
-FermionicOperator with only terra's Pauli stubbed (``tests/golden/make_reference_fixtures.py`` ->
+FermionicOperator / NumPyEigensolver / NumPyMinimumEigensolver with only terra's Pauli stubbed (``tests/golden/make_reference_fixtures.py`` ->
 ``tests/golden/reference_run.json``, checked by ``tests/test_reference_run.py``).  The per-Pauli CSR constructor itself lives in the
 un-vendored dependency ``qiskit-terra>=0.18.0`` (reference ``requirements.txt:1``), which is
 not installed here, so its published convention is restated:

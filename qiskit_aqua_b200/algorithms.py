@@ -125,8 +125,11 @@ class NumPyEigensolver:
             self._ret['eigvals'] = vals.astype(np.float64)
             self._ret['eigvecs'] = vecs
             return
+        # reference quirk (:171-173): for k >= 2^n - 1 the dense np.linalg.eig branch returns ALL 2^n
+        # eigenpairs (not truncated to k); aux operators are still evaluated for the first k only
+        k_eff = N if self._k >= N - 1 else self._k
         try:
-            r = eng.lanczos(k=self._k, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
+            r = eng.lanczos(k=k_eff, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
         except PsumError as ex:
             if ex.code == ERR_NOT_HERMITIAN:
                 raise AquaError('NumPyEigensolver on the GPU needs a Hermitian Pauli sum '
@@ -153,7 +156,7 @@ class NumPyEigensolver:
         self._ret['energies'] = np.array([np.real(v) for v in self._ret['eigvals']])
         if self._aux_operators:
             self._ret['aux_ops'] = [self._eval_aux_operators(self._ret['eigvecs'][i])
-                                    for i in range(len(self._ret['eigvals']))]
+                                    for i in range(min(self._k, len(self._ret['eigvals'])))]
 
     def compute_eigenvalues(self, operator=None, aux_operators=None):
         if operator is not None:

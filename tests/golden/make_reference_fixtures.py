@@ -9,6 +9,9 @@ everything else; only the reference files on the path are executed for real:
   qiskit/aqua/{aqua_error,aqua_globals,missing_optional_library_error}.py
   qiskit/optimization/applications/ising/{max_cut,common}.py
   qiskit/chemistry/fermionic_operator.py
+  qiskit/aqua/operators/{operator_base,primitive_ops/{primitive_op,pauli_op},list_ops/{list_op,summed_op},
+                         state_fns/*}.py  (opflow core, enough for to_opflow()/to_spmatrix())
+  qiskit/aqua/algorithms/{eigen_solvers/numpy_eigen_solver,minimum_eigen_solvers/numpy_minimum_eigen_solver}.py
 The package __init__ files of the reference are NOT executed (they import the whole of terra);
 synthetic parent packages give the relative imports something to hang on.
 """
@@ -48,12 +51,37 @@ def load_reference():
     mo = importlib.import_module('qiskit.aqua.missing_optional_library_error')
     aqua.AquaError, aqua.aqua_globals, aqua.MissingOptionalLibraryError = ae.AquaError, ag.aqua_globals, mo.MissingOptionalLibraryError
     ops = synth('qiskit.aqua.operators', REF + '/aqua/operators')
-    synth('qiskit.aqua.operators.legacy', REF + '/aqua/operators/legacy')
+    for sub in ('legacy', 'primitive_ops', 'list_ops', 'state_fns'):
+        synth('qiskit.aqua.operators.' + sub, REF + '/aqua/operators/' + sub)
+    # opflow core; operator_globals is synthetic (the real one builds gate circuits at import time)
+    og = types.ModuleType('qiskit.aqua.operators.operator_globals')
+    og.EVAL_SIG_DIGITS = 18
+    sys.modules[og.__name__] = og
+    ops.operator_globals = og
+    ops.OperatorBase = importlib.import_module('qiskit.aqua.operators.operator_base').OperatorBase
+    lb = importlib.import_module('qiskit.aqua.operators.legacy.base_operator')
+    ops.LegacyBaseOperator = sys.modules['qiskit.aqua.operators.legacy'].LegacyBaseOperator = lb.LegacyBaseOperator
+    ops.PrimitiveOp = importlib.import_module('qiskit.aqua.operators.primitive_ops.primitive_op').PrimitiveOp
+    ops.PauliOp = importlib.import_module('qiskit.aqua.operators.primitive_ops.pauli_op').PauliOp
+    ops.ListOp = importlib.import_module('qiskit.aqua.operators.list_ops.list_op').ListOp
+    ops.SummedOp = importlib.import_module('qiskit.aqua.operators.list_ops.summed_op').SummedOp
+    ops.StateFn = importlib.import_module('qiskit.aqua.operators.state_fns.state_fn').StateFn
+    for nm in ('vector_state_fn', 'operator_state_fn', 'dict_state_fn', 'circuit_state_fn'):
+        importlib.import_module('qiskit.aqua.operators.state_fns.' + nm)
+    og.I = ops.I = ops.PauliOp(terra_stub.Pauli('I'))
     from qiskit.aqua.operators.legacy.weighted_pauli_operator import WeightedPauliOperator
     from qiskit.aqua.operators.legacy.matrix_operator import MatrixOperator
     from qiskit.aqua.operators.legacy import op_converter
     ops.WeightedPauliOperator = WeightedPauliOperator
-    ops.StateFn = terra_stub.get_class('StateFn')
+    synth('qiskit.aqua.utils', REF + '/aqua/utils')
+    algs = synth('qiskit.aqua.algorithms', REF + '/aqua/algorithms')
+    algs.AlgorithmResult = importlib.import_module('qiskit.aqua.algorithms.algorithm_result').AlgorithmResult
+    algs.ClassicalAlgorithm = importlib.import_module('qiskit.aqua.algorithms.classical_algorithm').ClassicalAlgorithm
+    synth('qiskit.aqua.algorithms.eigen_solvers', REF + '/aqua/algorithms/eigen_solvers')
+    synth('qiskit.aqua.algorithms.minimum_eigen_solvers', REF + '/aqua/algorithms/minimum_eigen_solvers')
+    nes = importlib.import_module('qiskit.aqua.algorithms.eigen_solvers.numpy_eigen_solver')
+    algs.NumPyEigensolver = sys.modules['qiskit.aqua.algorithms.eigen_solvers'].NumPyEigensolver = nes.NumPyEigensolver
+    nmes = importlib.import_module('qiskit.aqua.algorithms.minimum_eigen_solvers.numpy_minimum_eigen_solver')
     synth('qiskit.optimization', REF + '/optimization')
     synth('qiskit.optimization.applications', REF + '/optimization/applications')
     synth('qiskit.optimization.applications.ising', REF + '/optimization/applications/ising')
@@ -65,6 +93,7 @@ def load_reference():
     from qiskit.chemistry.fermionic_operator import FermionicOperator
     return dict(WPO=WeightedPauliOperator, MatrixOperator=MatrixOperator, op_converter=op_converter,
                 common=common, max_cut=max_cut, FermionicOperator=FermionicOperator, aqua_globals=ag.aqua_globals,
+                NumPyEigensolver=nes.NumPyEigensolver, NumPyMinimumEigensolver=nmes.NumPyMinimumEigensolver,
                 AquaError=ae.AquaError)
 
 
@@ -77,7 +106,7 @@ def main():
     R = load_reference()
     WPO, Pauli = R['WPO'], terra_stub.Pauli
     out = {'note': 'outputs of the reference code itself (terra Pauli stubbed); see make_reference_fixtures.py',
-           'operators': [], 'maxcut': [], 'fermionic': []}
+           'operators': [], 'maxcut': [], 'fermionic': [], 'eigensolver': []}
     rng = np.random.default_rng(2024)
     for case in range(14):
         n = int(rng.integers(1, 7))
@@ -139,6 +168,43 @@ def main():
                                                                                for idx in zip(*np.nonzero(b))],
                                  'modes': int(a.shape[0]),
                                  'paulis': [[cplx(w), p.to_label()] for w, p in op.paulis]})
+    # NumPyEigensolver / NumPyMinimumEigensolver: all three branches (diagonal sort, dense eig,
+    # ARPACK eigs), aux operators, filters -- through the reference's own _run()
+    def aux_list(vals):
+        return None if vals is None else [[None if a is None else [float(a[0]), float(a[1])] for a in row] for row in vals]
+
+    H2 = [(-1.052373245772859, 'II'), (0.39793742484318045, 'ZI'), (-0.39793742484318045, 'IZ'),
+          (-0.01128010425623538, 'ZZ'), (0.18093119978423156, 'XX')]
+    AUX = [[(2.0, 'II')], [(0.5, 'II'), (0.5, 'ZZ'), (0.5, 'YY'), (-0.5, 'XX')]]
+    eig_cases = [('h2_k1', H2, 1, AUX, None), ('h2_k4', H2, 4, AUX, None), ('h2_k3_noaux', H2, 3, None, None),
+                 ('h2_filter', H2, 2, AUX, -1.0)]
+    r3 = np.random.default_rng(11)
+    for n, k in ((3, 2), (4, 3), (5, 1), (6, 4)):
+        labs = sorted({''.join(r3.choice(list('IXYZ')) for _ in range(n)) for _ in range(25)})
+        terms = [(float(r3.standard_normal()), l) for l in labs]
+        aux = [[(float(r3.standard_normal()), l) for l in labs[:5]], [(1.0, 'Z' * n)]]
+        eig_cases.append(('random_n%d_k%d' % (n, k), terms, k, aux, None))
+    for n, seed in ((4, 8123179999), (6, 99)):
+        w = R['common'].random_graph(n, weight_range=10, edge_prob=0.5, negative_weight=True, seed=seed)
+        op, _ = R['max_cut'].get_operator(w)
+        eig_cases.append(('maxcut_n%d' % n, [(complex(wt).real, pl.to_label()) for wt, pl in op.paulis], 2,
+                          [[(1.0, 'Z' + 'I' * (n - 1))]], None))
+    for name, terms, k, aux, thr in eig_cases:
+        op = WPO(paulis=[[w, Pauli(l)] for w, l in terms])
+        aux_ops = None if aux is None else [WPO(paulis=[[w, Pauli(l)] for w, l in a]) for a in aux]
+        fc = None if thr is None else (lambda x, v, a, t=thr: v >= t)
+        res = R['NumPyEigensolver'](op, k=k, aux_operators=aux_ops, filter_criterion=fc).run()
+        mres = R['NumPyMinimumEigensolver'](op, aux_operators=aux_ops, filter_criterion=fc).run()
+        vecs = [np.asarray(sf.primitive.data if hasattr(sf.primitive, 'data') and isinstance(sf.primitive.data, np.ndarray)
+                           else 0) for sf in res.eigenstates]
+        out['eigensolver'].append({
+            'name': name, 'terms': [[w, l] for w, l in terms], 'k': k,
+            'aux': None if aux is None else [[[w, l] for w, l in a] for a in aux], 'filter_ge': thr,
+            'eigenvalues': [cplx(v) for v in res.eigenvalues],
+            'aux_operator_eigenvalues': aux_list(res.aux_operator_eigenvalues),
+            'min_eigenvalue': None if mres.eigenvalue is None else cplx(mres.eigenvalue),
+            'min_aux': None if mres.aux_operator_eigenvalues is None else
+            [None if a is None else [float(a[0]), float(a[1])] for a in mres.aux_operator_eigenvalues]})
     path = os.path.join(HERE, 'reference_run.json')
     with open(path, 'w') as f:
         json.dump(out, f)

@@ -90,6 +90,12 @@ class Pauli:
         out.phase = (-e + getattr(self, 'phase', 0) + getattr(other, 'phase', 0)) % 4
         return out
 
+    def expand(self, other):       # other (x) self: `other` on the higher qubits
+        return Pauli((np.concatenate([self.z, other.z]), np.concatenate([self.x, other.x])))
+
+    def tensor(self, other):       # self (x) other: `self` on the higher qubits
+        return Pauli((np.concatenate([other.z, self.z]), np.concatenate([other.x, self.x])))
+
     def __getitem__(self, item):   # p[:] drops the phase (terra: a fresh label Pauli)
         return Pauli((self.z[item], self.x[item]))
 

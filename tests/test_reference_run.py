@@ -99,3 +99,57 @@ def test_kernels_vs_reference_run(case):
     y = op.engine.apply(psi).cpu().numpy()
     ref_y = np.array([_c(v) for v in rec['h_psi']])
     assert np.abs(y - ref_y).max() <= 1e-10 * max(1.0, np.abs(ref_y).max())
+
+
+def _aux_close(got, ref):
+    assert (got is None) == (ref is None)
+    if ref is None:
+        return
+    assert len(got) == len(ref)
+    for grow, rrow in zip(got, ref):
+        for a, b in zip(grow, rrow):
+            assert (a is None) == (b is None)
+            if b is not None:
+                assert abs(a[0] - b[0]) < 1e-9 and a[1] == b[1]
+
+
+@pytest.mark.parametrize('case', range(len(REF['eigensolver'])))
+def test_oracle_solve_vs_reference_eigensolver(case):
+    rec = REF['eigensolver'][case]
+    if rec['filter_ge'] is not None:
+        pytest.skip('filter logic is exercised through the product shim (GPU test)')
+    terms = po.simplify([(w, l) for w, l in rec['terms']])
+    val, vec = po.ref_solve(terms, k=rec['k'])
+    ref = np.array([_c(v) for v in rec['eigenvalues']])
+    np.testing.assert_allclose(np.sort(val.real), np.sort(ref.real), rtol=0, atol=1e-9)
+    if rec['aux'] is not None:
+        for i in range(min(rec['k'], len(ref))):
+            j = int(np.argmin(np.abs(val.real - ref[i].real)))
+            for a_terms, want in zip(rec['aux'], rec['aux_operator_eigenvalues'][i]):
+                got = po.ref_eval_aux(po.simplify([(w, l) for w, l in a_terms]), vec[j])
+                if abs(ref[i].real - np.delete(ref.real, i)).min() > 1e-6 if len(ref) > 1 else True:   # non-degenerate level
+                    assert abs(got[0] - want[0]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', range(len(REF['eigensolver'])))
+def test_product_eigensolvers_vs_reference_run(case):
+    pytest.importorskip('torch')
+    from qiskit_aqua_b200 import NumPyEigensolver, NumPyMinimumEigensolver
+    rec = REF['eigensolver'][case]
+    op = WeightedPauliOperator(paulis=[[w, Pauli(l)] for w, l in rec['terms']])
+    aux = None if rec['aux'] is None else [WeightedPauliOperator(paulis=[[w, Pauli(l)] for w, l in a]) for a in rec['aux']]
+    fc = None if rec['filter_ge'] is None else (lambda x, v, a, t=rec['filter_ge']: v >= t)
+    res = NumPyEigensolver(op, k=rec['k'], aux_operators=aux, filter_criterion=fc).run()
+    ref = np.array([_c(v) for v in rec['eigenvalues']])
+    assert len(res.eigenvalues) == len(ref)                  # incl. the k >= 2^n - 1 -> all 2^n quirk
+    np.testing.assert_allclose(np.real(res.eigenvalues), ref.real, rtol=0, atol=1e-9)
+    degenerate = len(ref) > 1 and np.min(np.diff(np.sort(ref.real))) < 1e-6
+    if rec['aux'] is not None and not degenerate:
+        got = [[None if a is None else (float(a[0]), a[1]) for a in row] for row in res.aux_operator_eigenvalues]
+        _aux_close(got, rec['aux_operator_eigenvalues'])
+    mres = NumPyMinimumEigensolver(op, aux_operators=aux, filter_criterion=fc).run()
+    assert abs(np.real(mres.eigenvalue) - rec['min_eigenvalue'][0]) < 1e-9
+    if rec['min_aux'] is not None and not degenerate:
+        for a, b in zip(mres.aux_operator_eigenvalues, rec['min_aux']):
+            assert abs(a[0] - b[0]) < 1e-8
