@@ -279,8 +279,9 @@ def main():
                 # the shim copies the pinned host state to the device (H2D) and reads the scalar back
                 if world == 1:
                     return op.evaluate_with_statevector(host)[0]
-                yv.copy_(host, non_blocking=True)            # y is not stored in this mode: reuse it
-                return eng.apply_sharded(yv, recv=recv, want_expect=True, store=False)[1]
+                # y is not stored in this mode: its buffer receives the shard; the copy is pipelined
+                # with the chunk-local passes (psum_expect_sharded_host)
+                return eng.expect_sharded_host(host, scratch=yv, recv=recv)
 
             e2e_step()
             barrier()
@@ -299,7 +300,7 @@ def main():
             e2e = {'value': T * float(1 << n_total) / (ms_e * 1e-3) / 1e9, 'unit': UNIT,
                    'h2d_bytes_per_step': 16 * N_loc * world, 'd2h_bytes_per_step': 16 * world,
                    'ms_per_step': ms_e, 'api': 'WeightedPauliOperator.evaluate_with_statevector'
-                   if world == 1 else 'PauliSumEngine.apply_sharded(host state, expectation only)',
+                   if world == 1 else 'PauliSumEngine.expect_sharded_host',
                    'energy': e_val.real}
 
     # ---- roofline -------------------------------------------------------------------------------

@@ -162,6 +162,11 @@ int psum_shard_terms(psum_handle_t h, int g, int64_t cap, uint64_t* x_local, uin
  * the all-reduced <psi|H|psi>. */
 int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
                        uint64_t recv_amps, double* expect_out, psum_stream_t stream);
+/* Sharded <psi|H|psi> for a shard that lives in HOST memory (the multi-GPU form of
+ * psum_expect_host): psi_dev receives the copy; the chunk-local passes of the local part follow the
+ * H2D copy chunk by chunk and the NCCL exchanges start when the last chunk has landed. */
+int psum_expect_sharded_host(psum_handle_t h, const void* psi_host, void* psi_dev, void* recv_dev,
+                             uint64_t recv_amps, double out[2], psum_stream_t stream);
 /* Host-side eigen-solver test hook (no device): which = 0 dense Jacobi (A = n*n), 1 tridiagonal
  * QL (A = d[n], e[n]).  w[n] ascending, V n*n eigenvectors in columns (may be NULL). */
 int psum_test_eigh(int which, int n, const double* A, double* w, double* V);

@@ -46,6 +46,7 @@ SIGNATURES = {
     'psum_apply_part': (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _dp, _vp]),
     'psum_shard_terms': (C.c_int, [_vp, C.c_int, C.c_int64, _u64p, _u64p, _dp, _i64p]),
     'psum_apply_sharded': (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, _dp, _vp]),
+    'psum_expect_sharded_host': (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, _dp, _vp]),
     'psum_allreduce_sum': (C.c_int, [_vp, _dp, C.c_int]),
     'psum_test_eigh': (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp]),
 }

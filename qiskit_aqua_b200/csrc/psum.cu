@@ -545,6 +545,9 @@ extern "C" int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], 
   return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, nullptr, out, (cudaStream_t)stream);
 }
 
+static int ensure_host_plan(psum_handle_s* h, int late);
+static int host_late_bits(const psum_handle_s* h);
+
 // <psi|H|psi> for a state that lives in HOST memory: the H2D copy is cut into 2^late_bits chunks
 // on a copy stream and every "early" pass (hi_bit inside a chunk) runs chunk by chunk as the data
 // arrives; only the passes that combine different chunks wait for the whole state.
@@ -558,22 +561,12 @@ extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t N = n_local_amps(h);
   const size_t bytes = N * sizeof(double2);
-  int late = 0;
-  if (h->n_loc >= 20 && h->opt.kernel != 1) late = std::min(4, h->n_loc - std::max(11, std::min(h->opt.tile_bits, kMaxTileBits)));
+  const int late = host_late_bits(h);
   if (late <= 0) {  // small state: one copy, then the ordinary expectation
     CUDA_TRY(cudaMemcpyAsync(psi_dev, psi_host, bytes, cudaMemcpyHostToDevice, st));
     return apply_local(h, (const double2*)psi_dev, (const double2*)psi_dev, nullptr, out, st);
   }
-  if (h->parts_h.empty() || h->late_bits_h != late) {
-    PlanOptions o = h->opt;
-    o.late_bits = late;
-    h->parts_h = build_parts(h->terms, h->n, 0, 0, o);
-    if (h->arena_h) cudaFree(h->arena_h);
-    h->arena_h = nullptr;
-    size_t need = 0;
-    PS_TRY(upload_plan(h, h->parts_h, &h->arena_h, &h->dparts_h, &need));
-    h->late_bits_h = late;
-  }
+  PS_TRY(ensure_host_plan(h, late));
   if (!h->copy_stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
@@ -904,37 +897,85 @@ extern "C" int psum_allreduce_sum(psum_handle_t h, double* host_vals, int n) {
 // Sharded H.psi: the local part runs on `stream` while the first partner shard is exchanged on the
 // communication stream; each further global part g alternates between the two halves of recv_dev
 // when it holds >= 2 shards, so exchange g+1 overlaps the passes over the shard of g.
-extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
-                                  uint64_t recv_amps, double* expect_out, psum_stream_t stream) {
-  if (!h || !psi_dev) return fail(PSUM_ERR_INVALID, "null argument");
-  if (!y_dev && !expect_out) return fail(PSUM_ERR_INVALID, "nothing to compute");
-  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
-  if (((uintptr_t)psi_dev | (uintptr_t)y_dev | (uintptr_t)recv_dev) & 15u)
-    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
-  PS_TRY(upload(h));
-  cudaStream_t st = (cudaStream_t)stream;
+// Builds (once) the chunk-friendly plan used when the state arrives from host memory.
+static int ensure_host_plan(psum_handle_s* h, int late) {
+  if (!h->parts_h.empty() && h->late_bits_h == late) return PSUM_OK;
+  PlanOptions o = h->opt;
+  o.late_bits = late;
+  h->parts_h = build_parts(h->terms, h->n, h->p_bits, h->rank, o);
+  if (h->arena_h) cudaFree(h->arena_h);
+  h->arena_h = nullptr;
+  size_t need = 0;
+  PS_TRY(upload_plan(h, h->parts_h, &h->arena_h, &h->dparts_h, &need));
+  h->late_bits_h = late;
+  return PSUM_OK;
+}
+
+static int host_late_bits(const psum_handle_s* h) {
+  if (h->n_loc < 20 || h->opt.kernel == 1) return 0;
+  return std::max(0, std::min(4, h->n_loc - std::max(11, std::min(h->opt.tile_bits, kMaxTileBits))));
+}
+
+// Sharded H.psi / <psi|H|psi>.  host_src != NULL: this rank's shard comes from host memory (y must
+// be NULL): the H2D copy is chunked on the copy stream, the chunk-local passes of the local part
+// follow it chunk by chunk, and the exchanges start when the last chunk has landed.
+static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void* recv_dev, uint64_t recv_amps,
+                        double* expect_out, cudaStream_t st, const void* host_src) {
   const uint64_t N = n_local_amps(h);
   const double2* psi = (const double2*)psi_dev;
   double2* y = (double2*)y_dev;
+  const int late = host_src ? host_late_bits(h) : 0;
+  if (host_src && late > 0) PS_TRY(ensure_host_plan(h, late));
+  const std::vector<DevPart>& parts = (host_src && late > 0) ? h->dparts_h : h->dparts;
   bool any_remote = false;
-  for (auto& D : h->dparts)
+  for (auto& D : parts)
     if (D.g != 0) any_remote = true;
   if (any_remote) {
     if (!h->comm) return fail(PSUM_ERR_NCCL, "terms with global x-parts need a communicator");
     if (!recv_dev || recv_amps < N) return fail(PSUM_ERR_INVALID, "recv_dev must hold one shard");
   }
-  // ring of receive buffers: up to nbuf exchanges are in flight ahead of the part being computed,
-  // so with enough buffers every exchange hides behind the (long) local part
+  // ring of receive buffers: up to nbuf exchanges are in flight ahead of the part being computed
   const int nbuf = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, recv_amps / std::max<uint64_t>(N, 1)));
   size_t pcount = 0;
   bool wrote_y = false;
+  const DevPart* local = nullptr;
+  std::vector<const DevPart*> remote;
+  for (auto& D : parts) {
+    if (D.g == 0) local = &D;
+    else remote.push_back(&D);
+  }
+  size_t n_early = 0;
+  if (host_src) {
+    // ---- chunked H2D + the chunk-local passes of the local part -------------------------------
+    if (!h->copy_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+    }
+    const uint64_t nchunks = 1ull << late;
+    for (uint64_t k = 0; k < nchunks; ++k)
+      if (!h->ev_chunk[k]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(h->ev_free, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
+    const size_t cbytes = (N * sizeof(double2)) >> late;
+    for (uint64_t k = 0; k < nchunks; ++k) {
+      CUDA_TRY(cudaMemcpyAsync((char*)psi_dev + k * cbytes, (const char*)host_src + k * cbytes, cbytes,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+      CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
+    }
+    const int cbits = h->n_loc - late;
+    if (local && late > 0)
+      while (n_early < local->passes.size() && local->passes[n_early].hi_bit < cbits) ++n_early;
+    for (uint64_t k = 0; k < nchunks; ++k) {
+      CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
+      if (n_early)
+        PS_TRY(run_part(h, *local, psi, psi, nullptr, 0, true, remote.empty() && n_early == local->passes.size(),
+                        &pcount, st, 0, n_early, k, nchunks));
+    }
+  }
   if (any_remote) {
-    CUDA_TRY(cudaEventRecord(h->ev_ready, st));
+    CUDA_TRY(cudaEventRecord(h->ev_ready, st));   // st has waited for every chunk by now
     CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
   }
-  std::vector<const DevPart*> remote;
-  for (auto& D : h->dparts)
-    if (D.g != 0) remote.push_back(&D);
   auto post_exchange = [&](const DevPart* D, int s, bool must_wait_used) -> int {
     if (must_wait_used) CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_used[s], 0));
     double2* buf = (double2*)recv_dev + (uint64_t)s * N;
@@ -949,12 +990,13 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
   size_t posted = 0;
   for (; posted < remote.size() && posted < (size_t)nbuf; ++posted)
     PS_TRY(post_exchange(remote[posted], (int)(posted % nbuf), false));
-  // local part (overlaps the exchanges posted above)
-  for (auto& D : h->dparts)
-    if (D.g == 0) {
-      PS_TRY(run_part(h, D, psi, psi, y, 0, expect_out != nullptr, remote.empty(), &pcount, st));
-      wrote_y = true;
-    }
+  // (rest of the) local part: overlaps the exchanges posted above
+  if (local) {
+    if (!host_src || n_early < local->passes.size() || local->passes.empty())
+      PS_TRY(run_part(h, *local, psi, psi, y, 0, expect_out != nullptr, remote.empty(), &pcount, st, n_early,
+                      (size_t)-1));
+    wrote_y = true;
+  }
   if (!wrote_y && y) CUDA_TRY(cudaMemsetAsync(y, 0, N * sizeof(double2), st));
   for (size_t r = 0; r < remote.size(); ++r) {
     const int slot = (int)(r % nbuf);
@@ -974,6 +1016,29 @@ extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_
     PS_TRY(fetch_scalars(h, 1, expect_out, st));
   }
   return PSUM_OK;
+}
+
+extern "C" int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* recv_dev,
+                                  uint64_t recv_amps, double* expect_out, psum_stream_t stream) {
+  if (!h || !psi_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!y_dev && !expect_out) return fail(PSUM_ERR_INVALID, "nothing to compute");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if (((uintptr_t)psi_dev | (uintptr_t)y_dev | (uintptr_t)recv_dev) & 15u)
+    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
+  PS_TRY(upload(h));
+  return sharded_impl(h, psi_dev, y_dev, recv_dev, recv_amps, expect_out, (cudaStream_t)stream, nullptr);
+}
+
+// Sharded <psi|H|psi> for a shard that lives in HOST memory (pinned for full speed); psi_dev
+// receives the copy.  The multi-GPU form of psum_expect_host.
+extern "C" int psum_expect_sharded_host(psum_handle_t h, const void* psi_host, void* psi_dev, void* recv_dev,
+                                        uint64_t recv_amps, double out[2], psum_stream_t stream) {
+  if (!h || !psi_host || !psi_dev || !out) return fail(PSUM_ERR_INVALID, "null argument");
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if (((uintptr_t)psi_dev | (uintptr_t)recv_dev) & 15u)
+    return fail(PSUM_ERR_INVALID, "state vectors must be 16-byte aligned");
+  PS_TRY(upload(h));
+  return sharded_impl(h, psi_dev, nullptr, recv_dev, recv_amps, out, (cudaStream_t)stream, psi_host);
 }
 
 #include "psum_lanczos.inc"

@@ -265,6 +265,19 @@ class PauliSumEngine:
                                     1 if accumulate else 0, ex if want_expect else None, _stream_ptr()))
         return complex(ex[0], ex[1])
 
+    def expect_sharded_host(self, psi_host, scratch, recv=None):
+        """All-reduced <psi|H|psi> for this rank's shard in HOST memory (psum_expect_sharded_host);
+        `scratch` is the device buffer that receives the shard."""
+        ptr, keep, n = _host_ptr(psi_host)
+        if n != self.n_local_amps or scratch.numel() < n:
+            raise ValueError('shard has %d amplitudes, expected %d' % (n, self.n_local_amps))
+        ex = (C.c_double * 2)()
+        check(lib().psum_expect_sharded_host(self._h, C.c_void_p(ptr), C.c_void_p(scratch.data_ptr()),
+                                             C.c_void_p(recv.data_ptr()) if recv is not None else None,
+                                             recv.numel() if recv is not None else 0, ex, _stream_ptr()))
+        del keep
+        return complex(ex[0], ex[1])
+
     def apply_sharded(self, psi, out=None, recv=None, want_expect=False, store=True):
         psi = as_device_state(psi, self.n_local_amps)
         if out is None and store:
@@ -276,6 +289,16 @@ class PauliSumEngine:
                                        recv.numel() if recv is not None else 0,
                                        ex if want_expect else None, _stream_ptr()))
         return (out, complex(ex[0], ex[1])) if want_expect else out
+
+
+def _host_ptr(psi_host):
+    if isinstance(psi_host, torch.Tensor):
+        t = psi_host
+        if t.dtype != torch.complex128 or not t.is_contiguous():
+            t = t.to(torch.complex128).contiguous()
+        return t.data_ptr(), t, t.numel()
+    a = np.ascontiguousarray(np.asarray(psi_host, dtype=np.complex128)).reshape(-1)
+    return a.ctypes.data, a, a.size
 
 
 def nccl_unique_id():

@@ -22,6 +22,7 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', torch.cuda.current_device()))
     ok = True
     for name, (n, x, z, y, c), opts in [
+            ('two_local_23q', W.two_local_random(23, 600, seed=23), {}),   # n_loc >= 20: chunked host path
             ('two_local_20q', W.two_local_random(20, 600, seed=20), {}),
             ('weight4_18q', W.random_weighted_paulis(18, 800, 4, seed=18), {}),
             ('dense_complex_14q', W.random_dense_paulis(14, 200, seed=3, complex_coeffs=True), {}),
@@ -37,6 +38,8 @@ def main():
         for rcv in (recv, recv[:2 * N_loc], recv[:N_loc]):   # ring of world-1, 2 and 1 shard buffers
             yv, ex = eng.apply_sharded(psi, recv=rcv, want_expect=True)
             _, ex2 = eng.apply_sharded(psi, recv=rcv, want_expect=True, store=False)
+            host = psi.cpu().pin_memory()
+            ex3 = eng.expect_sharded_host(host, scratch=torch.empty_like(psi), recv=rcv)
             gathered = [torch.empty_like(yv) for _ in range(world)]
             dist.all_gather(gathered, yv)
             if rank == 0:
@@ -46,7 +49,7 @@ def main():
                 err = np.abs(got - ref).max() / np.abs(ref).max()
                 eref = np.vdot(full, ref)
                 eerr = abs(ex - eref) / abs(eref)
-                eerr2 = abs(ex2 - eref) / abs(eref)
+                eerr2 = max(abs(ex2 - eref), abs(ex3 - eref)) / abs(eref)
                 good = err < 1e-10 and eerr < 1e-10 and eerr2 < 1e-10
                 ok &= good
                 print('%-18s world=%d parts=%d passes=%d  y err %.2e  <H> err %.2e / %.2e  %s' %
