@@ -12,6 +12,8 @@ everything else; only the reference files on the path are executed for real:
   qiskit/aqua/operators/{operator_base,primitive_ops/{primitive_op,pauli_op},list_ops/{list_op,summed_op},
                          state_fns/*}.py  (opflow core, enough for to_opflow()/to_spmatrix())
   qiskit/aqua/algorithms/{eigen_solvers/numpy_eigen_solver,minimum_eigen_solvers/numpy_minimum_eigen_solver}.py
+  qiskit/aqua/operators/{primitive_ops/matrix_op,list_ops/composed_op,expectations/matrix_expectation}.py
+  (terra's Statevector / quantum_info.Operator are functional minimal stubs: data + dims)
 The package __init__ files of the reference are NOT executed (they import the whole of terra);
 synthetic parent packages give the relative imports something to hang on.
 """
@@ -69,6 +71,29 @@ def load_reference():
     for nm in ('vector_state_fn', 'operator_state_fn', 'dict_state_fn', 'circuit_state_fn'):
         importlib.import_module('qiskit.aqua.operators.state_fns.' + nm)
     og.I = ops.I = ops.PauliOp(terra_stub.Pauli('I'))
+    # the rest of what the MatrixExpectation chain touches
+    for nm in ('composed_op', 'tensored_op'):
+        importlib.import_module('qiskit.aqua.operators.list_ops.' + nm)
+    ops.ComposedOp = sys.modules['qiskit.aqua.operators.list_ops.composed_op'].ComposedOp
+    ops.TensoredOp = sys.modules['qiskit.aqua.operators.list_ops.tensored_op'].TensoredOp
+    ops.MatrixOp = importlib.import_module('qiskit.aqua.operators.primitive_ops.matrix_op').MatrixOp
+    ops.CircuitOp = importlib.import_module('qiskit.aqua.operators.primitive_ops.circuit_op').CircuitOp
+    for cls, mod in (('VectorStateFn', 'vector_state_fn'), ('OperatorStateFn', 'operator_state_fn'),
+                     ('DictStateFn', 'dict_state_fn'), ('CircuitStateFn', 'circuit_state_fn')):
+        setattr(ops, cls, getattr(sys.modules['qiskit.aqua.operators.state_fns.' + mod], cls))
+    lo = sys.modules['qiskit.aqua.operators.list_ops']
+    lo.ListOp, lo.ComposedOp, lo.SummedOp, lo.TensoredOp = ops.ListOp, ops.ComposedOp, ops.SummedOp, ops.TensoredOp
+    sfm = sys.modules['qiskit.aqua.operators.state_fns']
+    for cls in ('StateFn', 'VectorStateFn', 'OperatorStateFn', 'DictStateFn', 'CircuitStateFn'):
+        setattr(sfm, cls, getattr(ops, cls))
+    pom = sys.modules['qiskit.aqua.operators.primitive_ops']
+    pom.PrimitiveOp, pom.PauliOp, pom.MatrixOp = ops.PrimitiveOp, ops.PauliOp, ops.MatrixOp
+    ops.Zero, ops.One = ops.StateFn('0'), ops.StateFn('1')
+    cv = synth('qiskit.aqua.operators.converters', REF + '/aqua/operators/converters')
+    cv.ConverterBase = importlib.import_module('qiskit.aqua.operators.converters.converter_base').ConverterBase
+    synth('qiskit.aqua.operators.expectations', REF + '/aqua/operators/expectations')
+    importlib.import_module('qiskit.aqua.operators.expectations.expectation_base')
+    mexp = importlib.import_module('qiskit.aqua.operators.expectations.matrix_expectation')
     from qiskit.aqua.operators.legacy.weighted_pauli_operator import WeightedPauliOperator
     from qiskit.aqua.operators.legacy.matrix_operator import MatrixOperator
     from qiskit.aqua.operators.legacy import op_converter
@@ -94,6 +119,7 @@ def load_reference():
     return dict(WPO=WeightedPauliOperator, MatrixOperator=MatrixOperator, op_converter=op_converter,
                 common=common, max_cut=max_cut, FermionicOperator=FermionicOperator, aqua_globals=ag.aqua_globals,
                 NumPyEigensolver=nes.NumPyEigensolver, NumPyMinimumEigensolver=nmes.NumPyMinimumEigensolver,
+                MatrixExpectation=mexp.MatrixExpectation, StateFn=ops.StateFn, ListOp=ops.ListOp, PauliOp=ops.PauliOp,
                 AquaError=ae.AquaError)
 
 
@@ -133,6 +159,9 @@ def main():
             hpsi = mat._matrix.dot(psi)
             rec['h_psi'] = [cplx(v) for v in hpsi]
             rec['to_dict'] = op.to_dict()
+            # opflow chain: MatrixExpectation.convert(~StateFn(H) @ StateFn(psi)).eval()
+            expr = ~R['StateFn'](op.to_opflow()) @ R['StateFn'](psi)
+            rec['matrix_expectation'] = cplx(R['MatrixExpectation']().convert(expr).eval())
             rec['chop_0.5'] = [[cplx(w), p.to_label()] for w, p in op.chop(0.5, copy=True).paulis]
         else:
             try:
@@ -205,6 +234,17 @@ def main():
             'min_eigenvalue': None if mres.eigenvalue is None else cplx(mres.eigenvalue),
             'min_aux': None if mres.aux_operator_eigenvalues is None else
             [None if a is None else [float(a[0]), float(a[1])] for a in mres.aux_operator_eigenvalues]})
+    # G5 table through the reference chain: <psi|P|psi> for P in X,Y,Z,I on |+>,|->,|0>,|1>,
+    # evaluated as one ListOp of states (matrix_op.py:199-201 broadcast)
+    sq = 1 / np.sqrt(2)
+    states = [[sq, sq], [sq, -sq], [1, 0], [0, 1]]
+    table = []
+    for lab in 'XYZI':
+        meas = ~R['StateFn'](R['PauliOp'](Pauli(lab)))
+        expr = meas @ R['ListOp']([R['StateFn'](np.array(v, dtype=complex)) for v in states])
+        vals = R['MatrixExpectation']().convert(expr).eval()
+        table.append([cplx(v) for v in vals])
+    out['matrix_expectation_table'] = {'paulis': 'XYZI', 'states': states, 'values': table}
     path = os.path.join(HERE, 'reference_run.json')
     with open(path, 'w') as f:
         json.dump(out, f)

@@ -100,6 +100,48 @@ class Pauli:
         return Pauli((self.z[item], self.x[item]))
 
 
+class Statevector:
+    """Functional minimum of terra's Statevector (what VectorStateFn touches)."""
+    def __init__(self, data, dims=None):
+        self.data = np.asarray(data.data if isinstance(data, Statevector) else data, dtype=complex).reshape(-1)
+    @property
+    def num_qubits(self): return int(round(np.log2(self.data.shape[0])))
+    @property
+    def dim(self): return self.data.shape[0]
+    def dims(self): return (2,) * self.num_qubits
+    def conjugate(self): return Statevector(np.conj(self.data))
+    def tensor(self, other): return Statevector(np.kron(self.data, other.data))
+    def __add__(self, other): return Statevector(self.data + other.data)
+    def __mul__(self, c): return Statevector(self.data * c)
+    __rmul__ = __mul__
+    def __eq__(self, other): return isinstance(other, Statevector) and np.allclose(self.data, other.data)
+    def __hash__(self): return 0
+    def to_dict(self): return {format(i, '0%db' % self.num_qubits): v for i, v in enumerate(self.data) if v != 0}
+
+
+class Operator:
+    """Functional minimum of terra's quantum_info.Operator (what MatrixOp touches)."""
+    def __init__(self, data, input_dims=None, output_dims=None):
+        self.data = np.asarray(data.data if isinstance(data, Operator) else data, dtype=complex)
+    @property
+    def num_qubits(self): return int(round(np.log2(self.data.shape[0])))
+    @property
+    def dim(self): return self.data.shape
+    def input_dims(self): return (2,) * int(round(np.log2(self.data.shape[1])))
+    def output_dims(self): return (2,) * int(round(np.log2(self.data.shape[0])))
+    def adjoint(self): return Operator(self.data.conj().T)
+    def conjugate(self): return Operator(self.data.conj())
+    def transpose(self): return Operator(self.data.T)
+    def tensor(self, other): return Operator(np.kron(self.data, other.data))
+    def compose(self, other, front=False): return Operator(self.data @ other.data if front else other.data @ self.data)
+    def dot(self, other): return Operator(self.data @ other.data)
+    def __add__(self, other): return Operator(self.data + other.data)
+    def __mul__(self, c): return Operator(self.data * c)
+    __rmul__ = __mul__
+    def __eq__(self, other): return isinstance(other, Operator) and np.allclose(self.data, other.data)
+    def __hash__(self): return 0
+
+
 SPECIAL = {
     ('qiskit.util', 'local_hardware_info'): lambda: {'cpus': 8, 'memory': 64, 'os': 'Linux'},
     ('qiskit.quantum_info', 'Pauli'): Pauli,
@@ -145,6 +187,10 @@ class StubModule(types.ModuleType):
             return SPECIAL[key]
         if name == 'Pauli':
             return Pauli
+        if name == 'Statevector':
+            return Statevector
+        if name == 'Operator':
+            return Operator
         if name == 'parallel_map':
             return _parallel_map
         if name[0].isupper() and not name.isupper():

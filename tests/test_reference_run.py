@@ -153,3 +153,39 @@ def test_product_eigensolvers_vs_reference_run(case):
     if rec['min_aux'] is not None and not degenerate:
         for a, b in zip(mres.aux_operator_eigenvalues, rec['min_aux']):
             assert abs(a[0] - b[0]) < 1e-8
+
+
+def test_oracle_matrix_expectation_vs_reference():
+    """~StateFn(H) is the measurement of H-dagger (state_fns/operator_state_fn.py adjoint), so the
+    reference chain yields conj(<psi|H|psi>) for complex weights."""
+    for rec in REF['operators']:
+        if 'matrix_expectation' not in rec:
+            continue
+        terms = po.simplify([(_c(w), lab) for w, lab in zip(rec['input_weights'], rec['input_labels'])])
+        adj = [(np.conj(w), lab) for w, lab in terms]
+        psi = np.array([_c(v) for v in rec['psi']])
+        assert abs(po.ref_matrix_expectation(adj, psi) - _c(rec['matrix_expectation'])) < 1e-12
+    tab = REF['matrix_expectation_table']
+    for lab, row in zip(tab['paulis'], tab['values']):
+        for vec, want in zip(tab['states'], row):
+            got = po.ref_matrix_expectation([(1.0, lab)], np.array(vec, dtype=complex))
+            assert abs(got - _c(want)) < 1e-15
+
+
+@pytest.mark.gpu
+def test_product_matrix_expectation_vs_reference_run():
+    pytest.importorskip('torch')
+    from qiskit_aqua_b200 import ListOp, MatrixExpectation, PauliOp, StateFn
+    for rec in REF['operators']:
+        if 'matrix_expectation' not in rec:
+            continue
+        op = WeightedPauliOperator(paulis=[[_c(w), Pauli(lab)] for w, lab in zip(rec['input_weights'], rec['input_labels'])])
+        psi = np.array([_c(v) for v in rec['psi']])
+        expr = ~StateFn(op.to_opflow()) @ StateFn(psi)
+        got = MatrixExpectation().convert(expr).eval()
+        assert abs(got - _c(rec['matrix_expectation'])) < 1e-10
+    tab = REF['matrix_expectation_table']
+    for lab, row in zip(tab['paulis'], tab['values']):
+        meas = ~StateFn(PauliOp(Pauli(lab)))
+        vals = MatrixExpectation().convert(meas @ ListOp([StateFn(np.array(v, dtype=complex)) for v in tab['states']])).eval()
+        np.testing.assert_allclose(vals, [_c(w) for w in row], atol=1e-12)
