@@ -12,6 +12,11 @@ from .operators import (AquaError, ComposedOp, I, ListOp, MatrixExpectation, Ope
                         X, Y, Z)
 from .algorithms import (EigensolverResult, MinimumEigensolverResult, NumPyEigensolver,  # noqa: F401,E402
                          NumPyMinimumEigensolver)
-from .applications import FermionicOperator, max_cut, random_graph, sample_most_likely  # noqa: F401,E402
+from .aqua_globals import aqua_globals  # noqa: F401,E402
+from .applications import FermionicOperator  # noqa: F401,E402
+from .ising import (clique, exact_cover, graph_partition, knapsack, max_cut, partition,  # noqa: F401,E402
+                    random_graph, sample_most_likely, set_packing, stable_set, tsp, vehicle_routing,
+                    vertex_cover)
+from . import ising  # noqa: F401,E402
 from .circuits import (VQE, CircuitStateFn, EfficientSU2, RealAmplitudes, StatevectorCircuit,  # noqa: F401,E402
                        energy_evaluation)

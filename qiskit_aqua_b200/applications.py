@@ -1,80 +1,16 @@
 """Input generators either side of the hot path, restated on bit masks (no Python 2^n loops).
 
-  * max_cut.get_operator / random_graph / sample_most_likely
-      qiskit/optimization/applications/ising/max_cut.py:31-54, common.py:23-60, :146-170
   * FermionicOperator(h1, h2).mapping('jordan_wigner')
       qiskit/chemistry/fermionic_operator.py:163-190, 344-474
+  * the Ising-problem generators (max_cut, ..., random_graph, sample_most_likely) live in
+    ising.py and are re-exported here
 """
 import itertools
 
 import numpy as np
 
+from .ising import max_cut, random_graph, sample_most_likely  # noqa: F401
 from .operators import Pauli, WeightedPauliOperator
-
-
-def random_graph(n, weight_range=10, edge_prob=0.3, negative_weight=True, savefile=None, seed=None):
-    """Erdos-Renyi graph with the reference's draw order (random <= p, integers, random >= .5)."""
-    assert weight_range >= 0
-    rng = np.random.default_rng(seed)
-    w = np.zeros((n, n))
-    m = 0
-    for i in range(n):
-        for j in range(i + 1, n):
-            if rng.random() <= edge_prob:
-                w[i, j] = rng.integers(1, weight_range)
-                if rng.random() >= 0.5 and negative_weight:
-                    w[i, j] *= -1
-                m += 1
-    w += w.T
-    if savefile:
-        with open(savefile, 'w', encoding='utf8') as f:
-            f.write('%d %d\n' % (n, m))
-            for i in range(n):
-                for j in range(i + 1, n):
-                    if w[i, j] != 0:
-                        f.write('%d %d %s\n' % (i + 1, j + 1, w[i, j]))
-    return w
-
-
-class max_cut:  # namespace mirroring the reference module name
-    @staticmethod
-    def get_operator(weight_matrix):
-        """0.5 w_ij Z_i Z_j for every edge, shift = -sum 0.5 w_ij."""
-        n = weight_matrix.shape[0]
-        paulis, shift = [], 0
-        for i in range(n):
-            for j in range(i):
-                if weight_matrix[i, j] != 0:
-                    paulis.append([0.5 * weight_matrix[i, j],
-                                   Pauli.from_masks(0, (1 << i) | (1 << j), n)])
-                    shift -= 0.5 * weight_matrix[i, j]
-        return WeightedPauliOperator(paulis=paulis), shift
-
-    @staticmethod
-    def max_cut_value(x, w):
-        xm = np.outer(x, (1 - x))
-        return np.sum(w * xm)
-
-    @staticmethod
-    def get_graph_solution(x):
-        return 1 - x
-
-
-def sample_most_likely(state_vector):
-    """Most likely bit string of a state vector (numpy or device tensor)."""
-    if hasattr(state_vector, 'device_vector'):
-        state_vector = state_vector.device_vector()
-    if hasattr(state_vector, 'is_cuda'):
-        k = int(state_vector.abs().argmax().item())
-        n = int(state_vector.numel()).bit_length() - 1
-    else:
-        n = int(np.log2(state_vector.shape[0]))
-        k = int(np.argmax(np.abs(state_vector)))
-    x = np.zeros(n)
-    for i in range(n):
-        x[i] = k % 2
-        k >>= 1
-    return x
 
 
 class FermionicOperator:

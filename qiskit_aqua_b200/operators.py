@@ -452,7 +452,8 @@ class _PauliSumMixin(OperatorBase):
 
     def _check_massive(self, method, matrix, num_qubits, massive):
         """operator_base.py:618-648: refuse dense conversions above 16 qubits unless massive."""
-        if num_qubits > 16 and not massive:
+        from .aqua_globals import aqua_globals
+        if num_qubits > 16 and not massive and not aqua_globals.massive:
             dim = 2 ** num_qubits
             if matrix:
                 obj_type = 'matrix'
