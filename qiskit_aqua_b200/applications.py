@@ -14,7 +14,7 @@ from .operators import Pauli, WeightedPauliOperator
 
 
 class FermionicOperator:
-    """Second-quantised operator -> qubit operator (Jordan-Wigner only on this path).
+    """Second-quantised operator -> qubit operator (jordan_wigner, parity, bravyi_kitaev).
     h2 uses the class's own convention h2[i,j,k,m] -> adag_i adag_k a_m a_j."""
 
     def __init__(self, h1, h2=None, ph_trans_shift=None):
@@ -44,12 +44,56 @@ class FermionicOperator:
              + 2 * bin(a[1] & b[0]).count('1')) % 4
         return (cx, cz), (1, 1j, -1, -1j)[e]
 
+    @staticmethod
+    def _mode_paulis(map_type, n):
+        """Per mode i the two Paulis (A_i, B_i) as (x_mask, z_mask), adag_i = (A_i - i B_i)/2,
+        a_i = (A_i + i B_i)/2 (fermionic_operator.py:163-342).
+
+          jordan_wigner  A = Z_0..Z_{i-1} X_i                    B = Z_0..Z_{i-1} Y_i
+          parity         A = Z_{i-1} X_i X_{i+1}..X_{n-1}        B = Y_i X_{i+1}..X_{n-1}
+          bravyi_kitaev  A = X_{U(i)} X_i Z_{P(i)}               B = X_{U(i)} Y_i Z_{P(i) minus F(i)}
+        with the update / parity / flip sets of the Fenwick tree over the next power of two,
+        restricted to the n modes present.
+        """
+        if map_type == 'jordan_wigner':
+            return [((1 << i, (1 << i) - 1), (1 << i, (1 << (i + 1)) - 1)) for i in range(n)]
+        if map_type == 'parity':
+            upper = (1 << n) - 1
+            return [((upper & ~((1 << i) - 1), (1 << (i - 1)) if i else 0),
+                     (upper & ~((1 << i) - 1), 1 << i)) for i in range(n)]
+        if map_type == 'bravyi_kitaev':
+            size = 1
+            while size < n:
+                size *= 2
+            keep = (1 << n) - 1
+            modes = []
+            for j in range(n):
+                update = parity = flip = 0
+                lo, span = 0, size                  # walk down the halving tree towards leaf j
+                while span > 1:
+                    half = span // 2
+                    if j - lo < half:
+                        update |= 1 << (lo + span - 1)      # the block's top node also stores this half
+                    else:
+                        parity |= 1 << (lo + half - 1)      # everything left of j inside this block
+                        if j == lo + span - 1:              # ... and j itself stores that left half
+                            flip |= 1 << (lo + half - 1)
+                        lo += half
+                    span = half
+                update &= keep
+                parity &= keep
+                flip &= keep
+                modes.append(((update | (1 << j), parity), (update | (1 << j), (parity & ~flip) | (1 << j))))
+            return modes
+        raise ValueError('Please specify the supported modes: jordan_wigner, parity, bravyi_kitaev, '
+                         'bksf')
+
     def mapping(self, map_type, threshold=1e-8):
-        if map_type.lower() != 'jordan_wigner':
-            raise ValueError('only the jordan_wigner mapping is provided on this path')
+        map_type = map_type.lower()
+        if map_type == 'bksf':
+            raise ValueError('the bksf (graph-based) encoding is not provided on this path')
         n = self._modes
-        # adag_i = (A_i - i B_i)/2, a_i = (A_i + i B_i)/2 with A = Z..ZX, B = Z..ZY
-        modes = [((1 << i, (1 << i) - 1), (1 << i, (1 << (i + 1)) - 1)) for i in range(n)]
+        modes = self._mode_paulis(map_type, n)
         acc, order = {}, []
 
         def add(key, w):
