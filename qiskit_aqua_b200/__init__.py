@@ -17,7 +17,8 @@ from .applications import FermionicOperator  # noqa: F401,E402
 from .ising import (clique, exact_cover, graph_partition, knapsack, max_cut, partition,  # noqa: F401,E402
                     random_graph, sample_most_likely, set_packing, stable_set, tsp, vehicle_routing,
                     vertex_cover)
-from . import fcidump, ising  # noqa: F401,E402
+from . import fcidump, ising, tapering  # noqa: F401,E402
+from .tapering import Z2Symmetries  # noqa: F401,E402
 from .fcidump import FCIDumpDriver, QiskitChemistryError, QMolecule  # noqa: F401,E402
 from .circuits import (VQE, CircuitStateFn, EfficientSU2, RealAmplitudes, StatevectorCircuit,  # noqa: F401,E402
                        energy_evaluation)
