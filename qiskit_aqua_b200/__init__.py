@@ -19,6 +19,7 @@ from .ising import (clique, exact_cover, graph_partition, knapsack, max_cut, par
                     vertex_cover)
 from . import fcidump, ising, tapering  # noqa: F401,E402
 from .tapering import Z2Symmetries  # noqa: F401,E402
+from .legacy import MatrixOperator, op_converter  # noqa: F401,E402
 from .fcidump import FCIDumpDriver, QiskitChemistryError, QMolecule  # noqa: F401,E402
 from .circuits import (VQE, CircuitStateFn, EfficientSU2, RealAmplitudes, StatevectorCircuit,  # noqa: F401,E402
                        energy_evaluation)

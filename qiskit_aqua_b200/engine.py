@@ -109,6 +109,13 @@ class PauliSumEngine:
         except Exception:  # interpreter shutdown
             pass
 
+    # a packed operator is immutable: copies of its owner share it (one handle, freed once)
+    def __copy__(self):
+        return self
+
+    def __deepcopy__(self, memo):
+        return self
+
     # -- introspection ------------------------------------------------------------------------
     def set_option(self, key, value):
         check(lib().psum_set_option(self._h, key.encode(), int(value)))
