@@ -13,6 +13,7 @@ No matrix (CSR or dense) is ever built: every evaluation is a matrix-free H.psi 
 import copy as _copy
 import json
 import numbers
+import operator as _operator
 
 import numpy as np
 
@@ -284,54 +285,121 @@ class WeightedPauliOperator(LegacyBaseOperator):
         return op
 
     def __eq__(self, other):
-        if not isinstance(other, WeightedPauliOperator) or len(self._paulis) != len(other._paulis):
+        """Equal after both sides are simplified (in place, as the reference does): same Paulis with
+        exactly equal weights (reference :147-166)."""
+        if not isinstance(other, WeightedPauliOperator):
             return False
-        mine = {p: w for w, p in self._paulis}
-        for w, p in other._paulis:
-            if p not in mine or not np.isclose(mine[p], w, atol=self._atol):
-                return False
-        return True
+        self.simplify()
+        other.simplify()
+        if len(self._paulis) != len(other._paulis):
+            return False
+        theirs = {p: w for w, p in other._paulis}
+        return all(p in theirs and theirs[p] == w for w, p in self._paulis)
 
-    def _add_or_sub(self, other, sign):
-        if self.is_empty():
-            return other.copy() if sign > 0 else other * -1.0
-        if other.is_empty():
-            return self.copy()
-        if self.num_qubits != other.num_qubits:
+    __hash__ = None
+
+    def _add_or_sub(self, other, operation, copy=True):
+        """Weights of Paulis present on both sides are combined in place, the others appended in
+        `other`'s order; zero results are kept until simplify()/chop() (reference :168-203)."""
+        if not self.is_empty() and not other.is_empty() and self.num_qubits != other.num_qubits:
             raise AquaError('Can not add/sub two operators with different number of qubits.')
-        return WeightedPauliOperator(paulis=[[w, p] for w, p in self._paulis] +
-                                     [[sign * w, p] for w, p in other._paulis], atol=self._atol)
+        ret = self.copy() if copy else self
+        table = {p: k for k, (_, p) in enumerate(ret._paulis)}
+        for w, p in other._paulis:
+            k = table.get(p)
+            if k is not None:
+                ret._paulis[k][0] = operation(ret._paulis[k][0], w)
+            else:
+                table[p] = len(ret._paulis)
+                ret._paulis.append([operation(0.0, w), p])
+        ret._engine = None
+        return ret
+
+    def add(self, other, copy=False):
+        return self._add_or_sub(other, _operator.add, copy=copy)
+
+    def sub(self, other, copy=False):
+        return self._add_or_sub(other, _operator.sub, copy=copy)
 
     def __add__(self, other):
-        return self._add_or_sub(other, 1.0)
-
-    def __sub__(self, other):
-        return self._add_or_sub(other, -1.0)
+        return self.add(other, copy=True)
 
     def __iadd__(self, other):
-        new = self._add_or_sub(other, 1.0)
-        self._paulis, self._engine = new._paulis, None
-        return self
+        return self.add(other, copy=False)
+
+    def __sub__(self, other):
+        return self.sub(other, copy=True)
+
+    def __isub__(self, other):
+        return self.sub(other, copy=False)
+
+    def _scaling_weight(self, scaling_factor, copy=False):
+        if not isinstance(scaling_factor, numbers.Number):
+            raise ValueError("Type of scaling factor is a valid type. {} if given.".format(scaling_factor.__class__))
+        ret = self.copy() if copy else self
+        ret._paulis = [[w * scaling_factor, p] for w, p in ret._paulis]
+        ret._engine = None
+        return ret
+
+    def multiply(self, other):
+        """self * other with the Pauli phases tracked; products are accumulated term by term, so
+        weights that cancel stay as zero entries until simplify() (reference :274-292)."""
+        ret = WeightedPauliOperator(paulis=[])
+        table = {}
+        for w1, p1 in self._paulis:
+            for w2, p2 in other._paulis:
+                p, ph = p1.dot(p2)
+                w = w1 * w2 * ph
+                if np.real(w) == 0.0 and np.imag(w) == 0.0:
+                    continue
+                k = table.get(p)
+                if k is not None:
+                    ret._paulis[k][0] = ret._paulis[k][0] + w
+                else:
+                    table[p] = len(ret._paulis)
+                    ret._paulis.append([0.0 + w, p])
+        return ret
 
     def __mul__(self, other):
         if isinstance(other, numbers.Number):
-            return WeightedPauliOperator(paulis=[[w * other, p] for w, p in self._paulis], atol=self._atol)
+            return self._scaling_weight(other, copy=True)
         if isinstance(other, WeightedPauliOperator):
-            out = []
-            for w1, p1 in self._paulis:
-                for w2, p2 in other._paulis:
-                    p, ph = p1.dot(p2)
-                    out.append([w1 * w2 * ph, p])
-            return WeightedPauliOperator(paulis=out, atol=self._atol)
+            return self.multiply(other)
         return NotImplemented
 
-    __rmul__ = __mul__
+    def __rmul__(self, other):
+        if isinstance(other, numbers.Number):
+            return self._scaling_weight(other, copy=True)
+        return NotImplemented
 
     def __neg__(self):
-        return self * -1.0
+        return self._scaling_weight(-1.0, copy=True)
+
+    def commute_with(self, other):
+        """[self, other] == 0 (reference :481-483, legacy/common.py:213-227)."""
+        com = self * other - other * self
+        com.simplify()
+        return bool(com.is_empty())
+
+    def anticommute_with(self, other):
+        com = self * other + other * self
+        com.simplify()
+        return bool(com.is_empty())
+
+    @property
+    def basis(self):
+        """Grouping info [(basis Pauli, [indices into paulis])]; ungrouped: every Pauli its own."""
+        if self._basis is None or len(self._basis) != len(self._paulis):
+            return [(p, [k]) for k, (_, p) in enumerate(self._paulis)]
+        return self._basis
+
+    def reorder_paulis(self):
+        """Ungrouped operator: the paulis as they are (reference :840-866)."""
+        return self._paulis
 
     def __str__(self):
-        return 'Representation: paulis, qubits: %d, size: %d' % (self.num_qubits, len(self._paulis))
+        name = '' if not self._name else '{}: '.format(self._name)
+        return '{}Representation: paulis, qubits: {}, size: {}'.format(name, self.num_qubits, len(self._paulis))
 
     def print_details(self):
         if self.is_empty():

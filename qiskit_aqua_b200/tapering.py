@@ -155,6 +155,8 @@ class Z2Symmetries:
             z2.tapering_values = values
             paulis = []
             for w, x, z in terms:
+                if np.real(w) == 0.0 and np.imag(w) == 0.0:
+                    continue                      # cancelled by the Clifford rotation: contributes no term
                 for bit, value in zip(touched, values):
                     if (x | z) & bit:
                         w = value * w

@@ -104,3 +104,107 @@ def test_jordan_wigner_generator_matches_oracle(golden_dir):
     ref = po.jordan_wigner(h1, h2)
     assert [(p.to_label()) for _, p in op.paulis] == [l for _, l in ref]
     np.testing.assert_allclose([w for w, _ in op.paulis], [w for w, _ in ref], atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own container tests (test/aqua/operators/legacy/test_weighted_pauli_operator.py)
+# ---------------------------------------------------------------------------------------------
+SIX = ['IXYZ', 'XXZY', 'IIZZ', 'XXYY', 'ZZXX', 'YYYY']
+
+
+def _term(label, w):
+    return WeightedPauliOperator(paulis=[[w, Pauli(label)]])
+
+
+def test_ref_from_to_file_num_qubits_is_empty_str(tmp_path):
+    weights = [0.2 + -1j * 0.8, 0.6 + -1j * 0.6, 0.8 + -1j * 0.2, -0.2 + -1j * 0.8, -0.6 - -1j * 0.6, -0.8 - -1j * 0.2]
+    op = WeightedPauliOperator.from_list([Pauli(x) for x in SIX], weights)
+    path = str(tmp_path / 'temp_op.json')
+    op.to_file(path)                                         # :61-73
+    assert WeightedPauliOperator.from_file(path) == op
+    empty = WeightedPauliOperator(paulis=[])
+    assert empty.num_qubits == 0 and empty.is_empty()        # :75-85
+    assert op.num_qubits == 4 and not op.is_empty()
+    op_a = _term('IXYZ', 0.5)
+    op_a += _term('ZYIX', 0.5)
+    assert str(op_a) == 'Representation: paulis, qubits: 4, size: 2'          # :87-101
+    assert str(WeightedPauliOperator(paulis=[[0.5, Pauli('IXYZ')]], name='ABC')) == \
+        'ABC: Representation: paulis, qubits: 4, size: 1'
+
+
+def test_ref_multiplication():
+    new_op = _term('IXYZ', 0.5) * _term('ZYIX', 0.5)         # :103-122
+    assert len(new_op.paulis) == 1
+    assert new_op.paulis[0][0] == -0.25 and new_op.paulis[0][1].to_label() == 'ZZYY'
+    new_op = -2j * new_op
+    assert new_op.paulis[0][0] == 0.5j
+    new_op = new_op * 0.3j
+    assert new_op.paulis[0][0] == -0.15
+
+
+def test_ref_add_sub_in_place_and_copy():
+    op_a, op_b = _term('IXYZ', 0.5), _term('ZYIX', 0.5)
+    ori_a, ori_b = op_a.copy(), op_b.copy()
+    op_a += op_b                                             # :124-146
+    assert op_a != ori_a and op_b == ori_b and len(op_a.paulis) == 2
+    op_a += _term('IXYZ', 0.25)
+    assert len(op_a.paulis) == 2 and op_a.paulis[0][0] == 0.75
+    op_a, op_b = _term('IXYZ', 0.5), _term('ZYIX', 0.5)
+    new_op = op_a + op_b                                     # :148-171
+    assert op_a == ori_a and op_b == ori_b and len(op_a.paulis) == 1 and len(new_op.paulis) == 2
+    new_op = new_op + _term('IXYZ', 0.25)
+    assert len(new_op.paulis) == 2 and new_op.paulis[0][0] == 0.75
+    new_op = op_a - op_b                                     # :173-198
+    assert op_a == ori_a and op_b == ori_b and len(new_op.paulis) == 2
+    assert new_op.paulis[0][0] == 0.5 and new_op.paulis[1][0] == -0.5
+    new_op = new_op - _term('IXYZ', 0.25)
+    assert len(new_op.paulis) == 2 and new_op.paulis[0][0] == 0.25
+    op_a -= op_b                                             # :200-222
+    assert op_a != ori_a and op_b == ori_b and len(op_a.paulis) == 2
+    op_a = _term('IXYZ', 0.5)
+    op_a -= _term('ZYIX', 0.5)
+    op_a -= _term('IXYZ', 0.5)
+    assert len(op_a.paulis) == 2                             # "sub does not remove zero weights"
+    with pytest.raises(AquaError):
+        _term('IXYZ', 1.0) + _term('XX', 1.0)
+
+
+def test_ref_equal_negation_simplify():
+    paulis = [Pauli(x) for x in SIX]
+    coeffs = [0.2, 0.6, 0.8, -0.2, -0.6, -0.8]
+    op1 = WeightedPauliOperator.from_list(paulis, coeffs)
+    op2 = WeightedPauliOperator.from_list(paulis, list(coeffs))
+    op3 = WeightedPauliOperator.from_list(paulis, [-c for c in coeffs])
+    op4 = WeightedPauliOperator.from_list(paulis, [-0.2, 0.6, 0.8, -0.2, -0.6, -0.8])
+    assert op1 == op2 and op1 != op3 and op1 != op4 and op3 != op4            # :224-240
+    assert op1 == -op3 and -op1 == op3                                          # :242-256
+    assert op1 * -1.0 == op3
+    new_op = _term('IXYZ', 0.5) + _term('IXYZ', -0.5)                           # :258-283
+    new_op.simplify()
+    assert len(new_op.paulis) == 0 and new_op.is_empty()
+    for i, pauli in enumerate(paulis):
+        op1 += WeightedPauliOperator(paulis=[[-coeffs[i], pauli]])
+        op1.simplify()
+        assert len(op1.paulis) == len(paulis) - (i + 1)
+    same = WeightedPauliOperator(paulis=[[0.5, Pauli('IXYZ')], [0.5, Pauli('IXYZ')]])   # :285-298
+    assert len(same.paulis) == 1 and len(same.basis) == 1 and same.basis[0][1][0] == 0
+
+
+@pytest.mark.parametrize('coeffs,counts', [
+    ([0.2, 0.6, 0.8, -0.2, -0.6, -0.8], [4, 2, 0]),                                                   # :300-315
+    ([0.2 + -0.5j, 0.6 - 0.3j, 0.8 - 0.6j, -0.5 + -0.2j, -0.3 + 0.6j, -0.6 + 0.8j], [6, 2, 0])])     # :317-334
+def test_ref_chop(coeffs, counts):
+    ori = WeightedPauliOperator.from_list([Pauli(x) for x in SIX], coeffs)
+    for threshold, num in zip([0.4, 0.7, 0.9], counts):
+        op = ori.copy()
+        op1 = op.chop(threshold=threshold, copy=True)
+        assert len(op.paulis) == 6 and len(op1.paulis) == num
+        op1 = op.chop(threshold=threshold, copy=False)
+        assert len(op.paulis) == num and len(op1.paulis) == num
+
+
+def test_commutation_helpers():
+    zz, xx, xi = _term('ZZ', 1.0), _term('XX', 2.0), _term('XI', 0.5)
+    assert zz.commute_with(xx) and not zz.commute_with(xi)
+    assert zz.anticommute_with(xi) and not zz.anticommute_with(xx)
+    assert zz.reorder_paulis() is zz.paulis
