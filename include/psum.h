@@ -67,6 +67,15 @@ int psum_info(psum_handle_t h, int64_t* info, int n_info);
 /* Free-bit set (bit mask over local qubits) and group count of pass p of global part g. */
 int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* n_groups,
                    int64_t* n_remote_groups, int64_t* n_patterns);
+/* Plan introspection, host only (no device needed): copies the device-facing arrays of pass p of
+ * global part g exactly as the kernels read them, so the planner can be verified without a GPU
+ * (tests/plan_interpreter.py).  counts: [0]=group records (48 B each) [1]=patterns [2]=component
+ * terms [3]=chunks (32 B each) [4]=tile bits L [5]=non-free local bits [6]=has imaginary patterns
+ * [7]=highest local qubit the pass combines.  Any buffer may be NULL (call once for the counts);
+ * pat_tptr holds patterns+1 entries.  Record layouts: qiskit_aqua_b200/csrc/psum_plan.h. */
+int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[8], void* groups,
+                     uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
+                     double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64]);
 
 /* ---- H.psi and <psi|H|psi> ------------------------------------------------------------ */
 /* y = H psi ; if expect_out != NULL also expect_out = {Re,Im} of sum_i conj(psi_i) y_i (host

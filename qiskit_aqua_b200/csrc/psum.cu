@@ -433,6 +433,40 @@ extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask
   return PSUM_OK;
 }
 
+// Plan introspection (host only): hands out the device-facing arrays of one pass exactly as the
+// kernels read them, so that the planner can be checked without a device (tests/plan_interpreter.py).
+extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[8], void* groups,
+                                uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
+                                double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64]) {
+  if (!h || !counts) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!h->planned) PS_TRY(plan(h));
+  PartHost* P = find_part(h, g);
+  if (!P || p < 0 || p >= (int)P->passes.size()) return fail(PSUM_ERR_INVALID, "no pass %d of part %d", p, g);
+  const PassHost& ps = P->passes[p];
+  counts[0] = (int64_t)ps.groups.size();
+  counts[1] = (int64_t)ps.pat_zt.size();
+  counts[2] = (int64_t)ps.term_val.size();
+  counts[3] = (int64_t)ps.chunks.size();
+  counts[4] = ps.L;
+  counts[5] = h->n_loc - ps.L;
+  counts[6] = ps.has_im ? 1 : 0;
+  counts[7] = ps.hi_bit;
+  if (groups) memcpy(groups, ps.groups.data(), ps.groups.size() * sizeof(GroupRec));
+  if (pat_zt) memcpy(pat_zt, ps.pat_zt.data(), ps.pat_zt.size() * sizeof(uint16_t));
+  if (pat_inl) memcpy(pat_inl, ps.pat_inl.data(), ps.pat_inl.size() * sizeof(uint16_t));
+  if (pat_tptr) memcpy(pat_tptr, ps.pat_tptr.data(), ps.pat_tptr.size() * sizeof(uint32_t));
+  if (term_zb) memcpy(term_zb, ps.term_zb.data(), ps.term_zb.size() * sizeof(uint64_t));
+  if (term_val) memcpy(term_val, ps.term_val.data(), ps.term_val.size() * sizeof(double));
+  if (chunks) memcpy(chunks, ps.chunks.data(), ps.chunks.size() * sizeof(ChunkRec));
+  if (fbit) memcpy(fbit, ps.fbit, 16);
+  if (nbit) {
+    int nj = 0;
+    for (int b = 0; b < h->n_loc; ++b)
+      if (!(ps.free_mask >> b & 1ull)) nbit[nj++] = (uint8_t)b;
+  }
+  return PSUM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch sequencing
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,165 @@
+"""Test infrastructure: a numpy interpreter for the pass plan that `k_pass` executes.
+
+`psum_plan_export` (include/psum.h) hands out, per pass, the very arrays the kernel reads -- group
+records, pattern z-masks, inline slots, term lists, chunk records, the free/non-free bit maps.
+`run_pass` below walks them the way the kernel does (csrc/psum_kernels.cuh: tile addressing, the
+fold of out-of-tile sign bits, loop A over inline "kind A" groups with its per-class order, loop B
+over class entry lists, remote groups, Hermitian pairing), so planner output can be checked against
+the oracle on the CPU.  It is a checker for the PLANNER's data, not a product path: nothing in
+qiskit_aqua_b200/ imports it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from qiskit_aqua_b200._lib import lib
+
+GROUP_DT = np.dtype([('xt', '<u4'), ('meta', '<u4'), ('zt0', '<u4'), ('zt1', '<u4'), ('cf0', '<f8'),
+                     ('cf1', '<f8'), ('xl', '<u8'), ('ent', '<u2', (4,))])
+CHUNK_DT = np.dtype([('g0', '<i4'), ('ng', '<i4'), ('p0', '<i4'), ('np', '<i4'), ('a_cnt', 'u1', (16,))])
+assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 32
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def export_pass(engine, g, p):
+    """Arrays of pass p of global part g, or None when there is no such pass."""
+    counts = (C.c_int64 * 8)()
+    rc = lib().psum_plan_export(engine._h, g, p, counts, None, None, None, None, None, None, None, None, None)
+    if rc != 0:
+        return None
+    ng, npat, nterm, nch, L, nnf, has_im, hi_bit = [int(v) for v in counts]
+    out = dict(L=L, n_nonfree=nnf, has_im=bool(has_im), hi_bit=hi_bit,
+               groups=np.zeros(ng, GROUP_DT), pat_zt=np.zeros(npat, np.uint16), pat_inl=np.zeros(npat, np.uint16),
+               pat_tptr=np.zeros(npat + 1, np.uint32), term_zb=np.zeros(nterm, np.uint64),
+               term_val=np.zeros(nterm, np.float64), chunks=np.zeros(nch, CHUNK_DT),
+               fbit=np.zeros(16, np.uint8), nbit=np.zeros(64, np.uint8))
+    rc = lib().psum_plan_export(engine._h, g, p, counts, _ptr(out['groups']), _ptr(out['pat_zt']), _ptr(out['pat_inl']),
+                                _ptr(out['pat_tptr']), _ptr(out['term_zb']), _ptr(out['term_val']), _ptr(out['chunks']),
+                                _ptr(out['fbit']), _ptr(out['nbit']))
+    assert rc == 0
+    return out
+
+
+def export_part(engine, g):
+    passes = []
+    while True:
+        ps = export_pass(engine, g, len(passes))
+        if ps is None:
+            return passes
+        passes.append(ps)
+
+
+def _parity(a):
+    return (np.bitwise_count(a) & 1).astype(np.int64)
+
+
+def _sign(a):
+    return 1.0 - 2.0 * _parity(a)
+
+
+def _deposit(values, positions):
+    """Bit j of every value goes to bit positions[j]."""
+    values = np.asarray(values, dtype=np.uint64)
+    out = np.zeros_like(values)
+    for j, pos in enumerate(positions):
+        out |= ((values >> np.uint64(j)) & np.uint64(1)) << np.uint64(pos)
+    return out
+
+
+def run_pass(ps, src, y=None, herm=False, check=True):
+    """Emulates one k_pass launch over all tiles.  Adds the pass's contribution to y (if given)
+    and returns sum conj(src_i) * contribution_i (with `herm`: the paired 2 Re z evaluation of the
+    Hermitian expectation kernels, imaginary part forced to zero as the kernel does)."""
+    L, nnf = ps['L'], ps['n_nonfree']
+    t = np.arange(1 << L, dtype=np.uint64)
+    t0 = t & ~np.uint64(0xE0)                      # the kernel's popc never sees the register bits
+    reg = ((t >> np.uint64(5)) & np.uint64(7)).astype(np.uint64)
+    off = _deposit(t, ps['fbit'][:L])
+    groups, chunks = ps['groups'], ps['chunks']
+    total = 0.0 + 0.0j
+    for tile_id in range(1 << nnf):
+        base = _deposit(np.array([tile_id], dtype=np.uint64), ps['nbit'][:nnf])[0]
+        idx = base | off
+        tile = src[idx]
+        acc = np.zeros(1 << L, dtype=np.complex128)
+
+        def add(G, D):
+            xt = int(G['xt']) & 0x7fffffff
+            remote = int(G['xt']) >> 31
+            hbit = int(G['meta']) >> 28
+            pv = src[idx ^ np.uint64(G['xl'])] if remote else tile[t ^ np.uint64(xt)]
+            if check and not remote:
+                # tile-local xor and the full local x mask describe the same partner
+                assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
+            if check and hbit:
+                assert not remote and xt and hbit - 1 >= 8 and (xt >> (hbit - 1)) == 1
+            contrib = D * pv
+            if herm and hbit:
+                contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
+            acc[:] += contrib
+
+        for ch in chunks:
+            ng, ng_a = int(ch['ng']) & 0xffff, int(ch['ng']) >> 16
+            p0, npat = int(ch['p0']), int(ch['np'])
+            grp = groups[int(ch['g0']):int(ch['g0']) + ng].copy()
+            cf = np.zeros(npat)
+            zt = np.zeros(npat, dtype=np.uint64)
+            for p in range(npat):                                             # the fold
+                gp = p0 + p
+                ta, tb = int(ps['pat_tptr'][gp]), int(ps['pat_tptr'][gp + 1])
+                v = float(np.sum(ps['term_val'][ta:tb] * _sign(ps['term_zb'][ta:tb] & base)))
+                zraw = int(ps['pat_zt'][gp])
+                if herm and zraw & 0x8000:
+                    v += v
+                cf[p], zt[p] = v, zraw & 0x7fff
+                inl = int(ps['pat_inl'][gp])
+                if inl != 0xffff:
+                    grp[inl >> 1]['cf1' if inl & 1 else 'cf0'] = v
+            g = 0
+            for cls in range(16):                                             # loop A
+                for _ in range(int(ch['a_cnt'][cls])):
+                    G = grp[g]
+                    if check:
+                        assert (int(G['meta']) >> 24) & 15 == cls and not int(G['xt']) >> 31
+                        assert ps['has_im'] or cls < 8
+                    s0 = G['cf0'] * _sign(t0 & np.uint64(G['zt0']))
+                    s1 = G['cf1'] * _sign(t0 & np.uint64(G['zt1']))
+                    flip = _sign(reg & np.uint64(cls & 7))
+                    add(G, s0 + s1 * flip if cls < 8 else s0 + 1j * s1 * flip)
+                    g += 1
+            assert g == ng_a
+            for g in range(ng_a, ng):                                         # loop B
+                G = grp[g]
+                meta = int(G['meta'])
+                p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
+                D = np.zeros(1 << L, dtype=np.complex128)
+                any_im = False
+                for e in range(nent):
+                    ent = int(G['ent'][e])
+                    cnt, cls = ent & 0xfff, ent >> 12
+                    s = np.zeros(1 << L)
+                    for j in range(cnt):
+                        if check:                       # class == register bits of the z-pattern
+                            assert (int(zt[p + j]) >> 5) & 7 == cls & 7
+                        s += cf[p + j] * _sign(t0 & zt[p + j])
+                    p += cnt
+                    any_im |= cls >= 8
+                    D += (1j if cls >= 8 else 1.0) * s * _sign(reg & np.uint64(cls & 7))
+                if check:
+                    assert bool(flat) == (nent == 1 and int(G['ent'][0]) >> 12 == 0)
+                    assert bool((meta >> 20) & 1) == any_im and (ps['has_im'] or not any_im)
+                add(G, D)
+        if y is not None:
+            y[idx] += acc
+        total += np.vdot(tile, acc)
+    return complex(total.real, 0.0) if herm else total
+
+
+def run_part(passes, src, y=None, herm=False):
+    total = 0.0 + 0.0j
+    for ps in passes:
+        total += run_pass(ps, src, y, herm=herm)
+    return total

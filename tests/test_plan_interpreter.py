@@ -1,0 +1,138 @@
+"""CPU verification of the pass planner: the arrays `k_pass` reads (exported with
+psum_plan_export) are executed by the numpy interpreter in tests/plan_interpreter.py and compared
+with the oracle -- tile addressing, fold lists, class entries, inline kind-A slots, chunking,
+sub-groups, remote groups, Hermitian pairing flags, late-bit plans and sharded parts."""
+import numpy as np
+import pytest
+
+from oracle import pauli_oracle as po
+from qiskit_aqua_b200.engine import PauliSumEngine
+
+from tests import plan_interpreter as pi
+
+
+def random_terms(n, T, rng, max_weight=4, complex_weights=True, x_pool=None, dense=0, no_y=False):
+    """Packed random Pauli terms; x_pool limits the distinct x-masks (many z-patterns per group)."""
+    x = np.zeros(T, dtype=np.uint64)
+    z = np.zeros(T, dtype=np.uint64)
+    for k in range(T):
+        if k < dense:
+            qs = rng.choice(n, size=min(n, 10), replace=False)
+        else:
+            qs = rng.choice(n, size=rng.integers(1, max_weight + 1), replace=False)
+        kinds = rng.integers(1, 4, size=len(qs))          # 1 X, 2 Y, 3 Z
+        if no_y:
+            kinds[kinds == 2] = 1
+        for q, kind in zip(qs, kinds):
+            if kind in (1, 2):
+                x[k] |= np.uint64(1) << np.uint64(q)
+            if kind in (2, 3):
+                z[k] |= np.uint64(1) << np.uint64(q)
+    if x_pool is not None:
+        pool = x[:x_pool].copy()
+        x = pool[rng.integers(0, x_pool, size=T)]
+        z = rng.integers(0, 1 << n, size=T, dtype=np.uint64)
+    ypow = np.array([bin(int(a) & int(b)).count('1') & 3 for a, b in zip(x, z)], dtype=np.uint8)
+    c = rng.standard_normal(T) + (1j * rng.standard_normal(T) if complex_weights else 0)
+    return x, z, ypow, c.astype(np.complex128)
+
+
+def random_state(n, rng):
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return psi / np.linalg.norm(psi)
+
+
+CASES = [
+    # n, T, options, generator kwargs
+    (11, 300, {'tile_bits': 11}, {}),
+    (12, 800, {'tile_bits': 11}, {}),
+    (13, 500, {'tile_bits': 11, 'low_bits': 4}, {'max_weight': 5}),
+    (13, 400, {'tile_bits': 12}, {'complex_weights': False}),
+    (12, 3000, {'tile_bits': 12}, {}),                                   # > 1024 patterns: several chunks
+    (12, 1500, {'tile_bits': 11}, {'x_pool': 6}),                        # many classes per group: sub-groups
+    (14, 200, {'tile_bits': 11}, {'dense': 12}),                         # x-masks no pass can hold: remote groups
+    (13, 600, {'tile_bits': 11, 'late_bits': 2}, {}),                    # host-state plan (early passes chunk-local)
+    (13, 300, {'tile_bits': 13}, {}),
+    (12, 600, {'tile_bits': 11}, {'no_y': True, 'complex_weights': False}),   # real-only passes (IM = false kernels)
+]
+
+
+@pytest.mark.parametrize('n,T,opts,kw', CASES, ids=['%dq-%dt-%s' % (c[0], c[1], '-'.join('%s%s' % kv for kv in c[2].items())) for c in CASES])
+def test_exported_plan_reproduces_oracle(n, T, opts, kw):
+    rng = np.random.default_rng(1000 * n + T)
+    x, z, ypow, c = random_terms(n, T, rng, **kw)
+    eng = PauliSumEngine(n, x, z, ypow, c, options=opts)
+    info = eng.info()
+    passes = pi.export_part(eng, 0)
+    assert len(passes) == info['n_passes'] > 0
+    assert sum(len(ps['groups']) for ps in passes) == info['n_group_records']
+    assert sum(len(ps['pat_zt']) for ps in passes) == info['n_patterns']
+    assert sum(len(ps['term_val']) for ps in passes) == info['n_component_terms']     # every term exactly once
+    if kw.get('dense'):
+        assert info['n_remote_groups'] > 0
+    if kw.get('no_y'):
+        assert not any(ps['has_im'] for ps in passes)
+    if kw.get('x_pool'):
+        assert info['n_group_records'] > info['n_xgroups']          # groups split into sub-groups
+    if T >= 3000:
+        assert max(len(ps['chunks']) for ps in passes) > 2         # staged in several chunks
+    if 'late_bits' in opts:      # early passes never combine amplitudes of different chunks
+        cbits = n - opts['late_bits']
+        early = [ps for ps in passes if ps['hi_bit'] < cbits]
+        assert early and all(ps['hi_bit'] < cbits for ps in passes[:len(early)])
+    psi = random_state(n, rng)
+    y = np.zeros(1 << n, dtype=np.complex128)
+    e = pi.run_part(passes, psi, y)
+    want = po.mf_apply(n, x, z, ypow, c, psi)
+    scale = np.linalg.norm(want)
+    assert np.linalg.norm(y - want) <= 1e-12 * scale
+    assert abs(e - np.vdot(psi, want)) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize('n,T,opts', [(11, 400, {'tile_bits': 11}), (13, 700, {'tile_bits': 11}), (12, 2500, {'tile_bits': 12})])
+def test_hermitian_pairing_flags(n, T, opts):
+    """Expectation with the pairing the HERM kernels use: groups flagged with a warp-uniform top
+    x bit are evaluated on half of the amplitudes with doubled patterns; equals Re <psi|H|psi>."""
+    rng = np.random.default_rng(77 * n + T)
+    x, z, ypow, c = random_terms(n, T, rng, complex_weights=False)
+    eng = PauliSumEngine(n, x, z, ypow, c, options=opts)
+    assert eng.info()['is_hermitian'] == 1
+    passes = pi.export_part(eng, 0)
+    flagged = sum(int(np.count_nonzero(ps['groups']['meta'] >> 28)) for ps in passes)
+    assert flagged > 0
+    for ps in passes:       # bit 15 of a stored pattern <=> its group is paired
+        for ch in ps['chunks']:
+            for G in ps['groups'][int(ch['g0']):int(ch['g0']) + (int(ch['ng']) & 0xffff)]:
+                first = int(ch['p0']) + (int(G['meta']) & 0xffff)
+                count = sum(int(e) & 0xfff for e in G['ent'][:(int(G['meta']) >> 16) & 7])
+                marked = ps['pat_zt'][first:first + count] >> 15
+                assert np.all(marked == (1 if int(G['meta']) >> 28 else 0))
+    psi = random_state(n, rng)
+    want = np.vdot(psi, po.mf_apply(n, x, z, ypow, c, psi))
+    got = pi.run_part(passes, psi, None, herm=True)
+    assert got.imag == 0.0 and abs(got.real - want.real) <= 1e-12 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_parts_reproduce_oracle(world):
+    """Every rank's parts (global x-part g: partner shard r ^ g, rank sign folded into the weights)
+    executed by the interpreter give that rank's slice of H.psi."""
+    n, T = 13, 500
+    rng = np.random.default_rng(5 + world)
+    x, z, ypow, c = random_terms(n, T, rng)
+    psi = random_state(n, rng)
+    want = po.mf_apply(n, x, z, ypow, c, psi)
+    n_loc = n - (world.bit_length() - 1)
+    shards = psi.reshape(world, 1 << n_loc)
+    seen_parts = set()
+    for rank in range(world):
+        eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11})
+        eng.shard(rank, world)
+        y = np.zeros(1 << n_loc, dtype=np.complex128)
+        for g in range(world):
+            passes = pi.export_part(eng, g)
+            if passes:
+                seen_parts.add(g)
+                pi.run_part(passes, shards[rank ^ g], y)
+        assert np.linalg.norm(y - want.reshape(world, -1)[rank]) <= 1e-12 * np.linalg.norm(want)
+    assert len(seen_parts) > 1
