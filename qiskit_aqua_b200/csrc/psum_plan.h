@@ -123,8 +123,8 @@ struct PlanOptions {
   int tile_bits = 12;
   int low_bits = 4;
   int min_cover = 3;
-  int plan_tries = 8;
-  int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)  // randomised greedy restarts of the pass planner; the cheapest plan wins
+  int plan_tries = 8;  // randomised greedy restarts of the pass planner; the cheapest plan wins
+  int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
 };
 
@@ -167,7 +167,7 @@ inline std::vector<MergedTerm> merge_terms(int64_t T, const uint64_t* x, const u
 
 // Greedy choice of free-bit sets.  masks = distinct local x-masks of one part.
 // Returns for each pass its free mask and the indices (into masks) it serves; groups that fit no
-// pass ("remote": partner tile read from global memory) are appended to pass 0.
+// pass ("remote": partner amplitudes read from global memory) are appended to the LAST pass.
 struct PassChoice {
   uint64_t free_mask;
   std::vector<int> members;
