@@ -136,3 +136,30 @@ def test_sharded_parts_reproduce_oracle(world):
                 pi.run_part(passes, shards[rank ^ g], y)
         assert np.linalg.norm(y - want.reshape(world, -1)[rank]) <= 1e-12 * np.linalg.norm(want)
     assert len(seen_parts) > 1
+
+
+@pytest.mark.parametrize('kind', ['c4_style', 'molecular', 'c5_style'])
+def test_bench_workload_shapes(kind):
+    """The benchmark operator families at 13-14 qubits: TFIM + Heisenberg + 3-local part (C4),
+    Jordan-Wigner molecular-style sum (C3), random weight <= 4 Paulis (C5)."""
+    from qiskit_aqua_b200 import workloads as W
+    if kind == 'c4_style':
+        n = 13
+        _, x, z, ypow, c = W.ising_heisenberg(n, n_triples=1500, seed=30)
+    elif kind == 'molecular':
+        _, x, z, ypow, c = W.molecular_style(12)
+        n = 12
+    else:
+        n = 14
+        _, x, z, ypow, c = W.random_weighted_paulis(n, 2000, 4, seed=34)
+    eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11})
+    passes = pi.export_part(eng, 0)
+    rng = np.random.default_rng(3)
+    psi = random_state(n, rng)
+    y = np.zeros(1 << n, dtype=np.complex128)
+    pi.run_part(passes, psi, y)
+    want = po.mf_apply(n, x, z, ypow, np.asarray(c, dtype=np.complex128), psi)
+    assert np.linalg.norm(y - want) <= 1e-12 * np.linalg.norm(want)
+    if eng.info()['is_hermitian']:
+        e = pi.run_part(passes, psi, None, herm=True)
+        assert abs(e.real - np.vdot(psi, want).real) <= 1e-11 * max(1.0, abs(np.vdot(psi, want)))
