@@ -36,6 +36,110 @@ class FermionicOperator:
     def h2(self):
         return self._h2
 
+    @h1.setter
+    def h1(self, new_h1):
+        self._h1 = new_h1
+
+    @h2.setter
+    def h2(self, new_h2):
+        self._h2 = new_h2
+
+    def __eq__(self, other):
+        return bool(np.all(self._h1 == other._h1) and np.all(self._h2 == other._h2))
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    # -- basis changes and mode reduction (fermionic_operator.py:126-160, 533-617) -----------------
+    def transform(self, unitary_matrix):
+        """h1 -> U^dag h1 U, h2[i,j,k,l] -> sum conj(U_ia) U_jb conj(U_kc) U_ld h2[i,j,k,l]."""
+        u = np.asarray(unitary_matrix)
+        self._h1 = u.T.conj().dot(self._h1.dot(u))
+        self._h2 = np.einsum('ia,jb,kc,ld,ijkl->abcd', u.conj(), u, u.conj(), u, self._h2, optimize=True)
+
+    def fermion_mode_elimination(self, fermion_mode_array):
+        """Drop the listed modes (rows/columns of h1 and h2)."""
+        keep = np.setdiff1d(np.arange(self._modes), np.asarray(fermion_mode_array))
+        h1_new = self._h1[np.ix_(keep, keep)].copy()
+        if np.count_nonzero(self._h2) > 0:
+            h2_new = self._h2[np.ix_(keep, keep, keep, keep)].copy()
+        else:
+            h2_new = np.zeros((len(keep),) * 4)
+        return FermionicOperator(h1_new, h2_new)
+
+    def fermion_mode_freezing(self, fermion_mode_array):
+        """Treat the listed modes as occupied: their interaction with the kept modes is folded
+        into h1, their own energy into the returned shift.  With F the frozen and K the kept modes
+        (h2 indexed [i, j, l, k] as in the reference):
+            h1[l, j] -= sum_{i in F} h2[i, j, l, i]      h1[l, k] += sum_{i in F} h2[i, i, l, k]
+            h1[i, j] += sum_{l in F} h2[i, j, l, l]      h1[i, k] -= sum_{l in F} h2[i, l, l, k]
+            shift = sum_{i != l in F} (h2[i, i, l, l] - h2[i, l, l, i]) + sum_{i in F} h1[i, i]
+        """
+        frozen = np.sort(np.asarray(fermion_mode_array))
+        keep = np.setdiff1d(np.arange(self._modes), frozen)
+        h_1 = self._h1.copy()
+        h2 = self._h2
+        energy_shift = 0.0
+        h2_new = np.zeros((len(keep),) * 4)
+        if np.count_nonzero(h2) > 0:
+            h2_new = h2[np.ix_(keep, keep, keep, keep)].copy()
+            kk = np.ix_(keep, keep)
+            f = frozen
+            # h2[i, j, l, i] summed over frozen i -> [j, l]; transposed onto h1[l, j]
+            h_1[kk] -= np.einsum('ijli->lj', h2[np.ix_(f, keep, keep, f)])
+            h_1[kk] += np.einsum('iilk->lk', h2[np.ix_(f, f, keep, keep)])
+            h_1[kk] += np.einsum('ijll->ij', h2[np.ix_(keep, keep, f, f)])
+            h_1[kk] -= np.einsum('illk->ik', h2[np.ix_(keep, f, f, keep)])
+            ff = h2[np.ix_(f, f, f, f)]
+            coulomb = np.einsum('iill->il', ff)
+            exchange = np.einsum('illi->il', ff)
+            off = ~np.eye(len(f), dtype=bool)
+            energy_shift += float(np.sum(coulomb[off]) - np.sum(exchange[off]))
+        energy_shift += np.sum(np.diagonal(h_1)[frozen])
+        return FermionicOperator(h_1[np.ix_(keep, keep)], h2_new), energy_shift
+
+    # -- observables used as aux operators of the eigensolver (fermionic_operator.py:619-760) -------
+    def total_particle_number(self):
+        n = self._modes
+        return FermionicOperator(np.eye(n, dtype=complex), np.zeros((n,) * 4))
+
+    def total_magnetization(self):
+        """(N_up - N_down)/2 in block spin order (first half up)."""
+        n = self._modes
+        h1 = np.eye(n, dtype=complex) * 0.5
+        h1[n // 2:, n // 2:] *= -1.0
+        return FermionicOperator(h1, np.zeros((n,) * 4))
+
+    def total_angular_momentum(self):
+        """S^2 = S_x^2 + S_y^2 + S_z^2 for block spin order, assembled with index arrays:
+        orbital p has the modes (p, p + m), m = modes / 2."""
+        n = self._modes
+        m = n // 2
+        h1 = np.zeros((n, n))
+        h2 = np.zeros((n,) * 4)
+        p, q = np.indices((m, m)).reshape(2, -1)
+        d = p == q
+        a, b = p[~d], q[~d]                      # different orbitals
+        o = p[d]                                 # same orbital
+        # S_x^2 + S_y^2: the spin-flip pairs; the p(up)p(down) q(up)q(down) terms cancel between x and y
+        h2[a + m, a, b, b + m] += 2.0
+        h2[a, a + m, b + m, b] += 2.0
+        # S_z^2
+        h2[a, a, b, b] += 1.0
+        h2[a + m, a + m, b, b] -= 1.0
+        h2[a, a, b + m, b + m] -= 1.0
+        h2[a + m, a + m, b + m, b + m] += 1.0
+        # same orbital: number-operator products
+        h2[o, o, o + m, o + m] -= 2.0
+        h2[o + m, o + m, o, o] -= 2.0
+        h2[o, o + m, o + m, o] += 1.0
+        h2[o + m, o, o, o + m] += 1.0
+        h1[o, o] += 3.0
+        h1[o + m, o + m] += 3.0
+        return FermionicOperator(h1=h1 * 0.25, h2=h2 * 0.25)
+
     @staticmethod
     def _mul(a, b):
         """(x,z,phase) product of two label Paulis given as (x, z)."""
