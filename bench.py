@@ -181,7 +181,7 @@ def main():
     import torch
     import torch.distributed as dist
     from qiskit_aqua_b200 import PauliSumEngine, WeightedPauliOperator, fill_state, nccl_unique_id
-    from qiskit_aqua_b200.engine import as_device_state, vec_dot, vec_scale
+    from qiskit_aqua_b200.engine import vec_dot, vec_scale
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

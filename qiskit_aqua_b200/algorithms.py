@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from ._lib import ERR_NOT_HERMITIAN, PsumError
-from .operators import (AquaError, LegacyBaseOperator, ListOp, OperatorBase, StateFn, SummedOp,
-                        WeightedPauliOperator, _PauliSumMixin, _terms_of)
+from .operators import (AquaError, LegacyBaseOperator, ListOp, StateFn, WeightedPauliOperator,
+                        _PauliSumMixin, _terms_of)
 
 
 class AlgorithmResult(dict):

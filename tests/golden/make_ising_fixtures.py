@@ -14,7 +14,6 @@ import itertools
 import json
 import os
 import sys
-import types
 
 import numpy as np
 

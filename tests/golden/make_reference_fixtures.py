@@ -17,7 +17,6 @@ everything else; only the reference files on the path are executed for real:
 The package __init__ files of the reference are NOT executed (they import the whole of terra);
 synthetic parent packages give the relative imports something to hang on.
 """
-import itertools
 import json
 import os
 import sys

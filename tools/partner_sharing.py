@@ -2,7 +2,7 @@
 the register bits of a pass reused one set of 8 partner amplitudes ("load sets" vs groups).
 See DESIGN.md, candidates for the next round."""
 import sys, itertools; import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, bench
+import bench
 from qiskit_aqua_b200.engine import PauliSumEngine
 from qiskit_aqua_b200 import workloads as W
 def analyse(name, n, x, z, y, c, nreg=3):
