@@ -942,6 +942,22 @@ static int ensure_host_plan(psum_handle_s* h, int late) {
   size_t need = 0;
   PS_TRY(upload_plan(h, h->parts_h, &h->arena_h, &h->dparts_h, &need));
   h->late_bits_h = late;
+  // the chunked path launches every chunk-local pass once per chunk, each launch with its own
+  // block of partials: grow the partial buffer when a large plan needs more than upload() reserved
+  size_t need_h = 0;
+  const size_t nchunks = (size_t)1 << late;
+  const int cbits = h->n_loc - late;
+  for (const DevPart& D : h->dparts_h) {
+    need_h += (size_t)D.grid_stream;
+    for (const DevPass& dp : D.passes) need_h += (size_t)dp.grid * (dp.hi_bit < cbits ? nchunks : 1);
+  }
+  if (need_h + 4096 > h->partial_cap) {
+    CUDA_TRY(cudaDeviceSynchronize());  // earlier launches may still read the old buffer
+    if (h->d_partial) cudaFree(h->d_partial);
+    h->d_partial = nullptr;
+    h->partial_cap = need_h + 4096;
+    CUDA_TRY(cudaMalloc(&h->d_partial, h->partial_cap * sizeof(double2)));
+  }
   return PSUM_OK;
 }
 
