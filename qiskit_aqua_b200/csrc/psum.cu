@@ -275,7 +275,8 @@ static int upload(psum_handle_s* h) {
   CUDA_TRY(cudaMalloc(&h->d_partial, h->partial_cap * sizeof(double2)));
   CUDA_TRY(cudaMalloc(&h->d_scalar, 256 * sizeof(double2)));
   CUDA_TRY(cudaMallocHost(&h->h_scalar, 256 * sizeof(double2)));
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};  // function attributes are per device
+  bool& attr_done = attr_done_dev[h->device >= 0 && h->device < 64 ? h->device : 0];
   if (!attr_done) {
     int max_smem = (int)pass_smem_bytes(kMaxTileBits);
 #define SET_SMEM(S, E, I)                                                                              \
