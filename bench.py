@@ -49,6 +49,7 @@ def parse_args():
                     help='c4: Ising+Heisenberg+3-local (headline); c5: random weight<=4 Pauli sum')
     ap.add_argument('--tile-bits', type=int, default=0)
     ap.add_argument('--low-bits', type=int, default=0)
+    ap.add_argument('--reg-bits', type=int, default=0)
     return ap.parse_args()
 
 
@@ -204,6 +205,8 @@ def main():
         opts['tile_bits'] = args.tile_bits
     if args.low_bits:
         opts['low_bits'] = args.low_bits
+    if args.reg_bits:
+        opts['reg_bits'] = args.reg_bits
     eng = PauliSumEngine(n_total, x, z, y, c, opts)
     recv = None
     if world > 1:

@@ -229,6 +229,46 @@ def mf_expect(n, x_mask, z_mask, ypow, coeff, psi) -> complex:
     return complex(np.vdot(psi, mf_apply(n, x_mask, z_mask, ypow, coeff, psi)))
 
 
+def product_state(n: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """|psi> = prod_q (a_q |0> + b_q |1>) as a dense vector (qubit q <-> bit q); small n only."""
+    psi = np.ones(1, dtype=np.complex128)
+    for q in range(n):
+        psi = np.concatenate([a[q] * psi, b[q] * psi])
+    return psi
+
+
+def product_state_expect(n: int, x_mask, z_mask, ypow, coeff, a: np.ndarray, b: np.ndarray) -> complex:
+    """<psi|H|psi> for the product state above WITHOUT any 2^n object: a size-independent parity
+    property of the path.  A label Pauli factorises, <P> = prod_q <sigma_q>, with
+    <X> = 2 Re(conj(a) b), <Y> = 2 Im(conj(a) b), <Z> = |a|^2 - |b|^2; a packed term is
+    c (-i)^{ypow - nY} times its label Pauli (same convention as mf_apply)."""
+    a = np.asarray(a, dtype=np.complex128)
+    b = np.asarray(b, dtype=np.complex128)
+    ex = 2.0 * (np.conj(a) * b).real
+    ey = 2.0 * (np.conj(a) * b).imag
+    ez = np.abs(a) ** 2 - np.abs(b) ** 2
+    norm = float(np.prod(np.abs(a) ** 2 + np.abs(b) ** 2))
+    phase = np.array([1, -1j, -1, 1j], dtype=np.complex128)
+    total = 0.0 + 0.0j
+    for x, z, yp, c in zip(x_mask, z_mask, ypow, coeff):
+        x, z = int(x), int(z)
+        v = 1.0
+        ny = 0
+        for q in range(n):
+            xb, zb = (x >> q) & 1, (z >> q) & 1
+            if xb and zb:
+                v *= ey[q]
+                ny += 1
+            elif xb:
+                v *= ex[q]
+            elif zb:
+                v *= ez[q]
+            else:
+                v *= abs(a[q]) ** 2 + abs(b[q]) ** 2
+        total += complex(c) * phase[(int(yp) - ny) & 3] * v
+    return total if norm else 0.0
+
+
 def mf_diag(n, z_mask, coeff) -> np.ndarray:
     """diagonal of an all-Z sum (branch numpy_eigen_solver.py:163-169)."""
     idx = np.arange(1 << n, dtype=np.uint64)

@@ -7,12 +7,17 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/psum.h"
 #include "psum_eig.h"
+#define PSUM_SMALL_KERNELS
 #include "psum_kernels.cuh"
+#include "psum_kpass.h"
 #include "psum_plan.h"
 
 using namespace psum;
@@ -98,6 +103,7 @@ struct DevPass {
   PassParams params;
   bool has_im = false;
   int hi_bit = 0;
+  int rb = 3;
   int threads = 256;
   int grid = 0;
   size_t smem = 0;
@@ -138,6 +144,19 @@ struct psum_handle_s {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[256] = {nullptr};
   cudaEvent_t ev_free = nullptr;
+  // pageable host input: ring of pinned staging buffers filled by host threads ahead of the DMA
+  static constexpr int kBounceSlots = 4;
+  char* bounce_buf[kBounceSlots] = {nullptr};
+  cudaEvent_t bounce_done[kBounceSlots] = {nullptr};
+  size_t bounce_bytes = 0;
+  int bounce_next = 0;
+  int copy_threads = 0;     // 0 = auto
+  // exchange instrumentation (option "profile_exchange") and the compute-only mode used to measure
+  // how much of the exchange hides behind the passes (option "skip_exchange")
+  int profile_exchange = 0, skip_exchange = 0;
+  std::vector<cudaEvent_t> ex_ev;   // start/stop pairs on comm_stream
+  int ex_count = 0;
+  double ex_stats[4] = {0, 0, 0, 0};
   // sharding
   nccl_comm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
@@ -170,10 +189,7 @@ static int plan(psum_handle_s* h) {
   return PSUM_OK;
 }
 
-static size_t pass_smem_bytes(int L) {
-  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 32 + sizeof(GroupRec) * (kGrpChunk + 1) +
-         16 * 16 + 8 * 9 * 64;
-}
+static size_t pass_smem_bytes(int L) { return pass_smem_bytes_c(L); }
 
 template <typename T>
 static T* arena_put(char* base, size_t& off, const std::vector<T>& v, std::vector<char>& host) {
@@ -212,6 +228,7 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
       for (const PassHost& ph : P.passes) {
         DevPass dp;
         memset(&dp.params, 0, sizeof(dp.params));
+        dp.params.bundles = arena_put(base, off, ph.bundles, host);
         dp.params.groups = arena_put(base, off, ph.groups, host);
         dp.params.pat_zt = arena_put(base, off, ph.pat_zt, host);
         dp.params.pat_inl = arena_put(base, off, ph.pat_inl, host);
@@ -229,16 +246,18 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
         for (int b = 0; b < h->n_loc; ++b)
           if (!(ph.free_mask >> b & 1ull)) dp.params.nbit[nj++] = (uint8_t)b;
         for (int j = 0; j < ph.L; ++j) dp.params.fbit[j] = ph.fbit[j];
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < (1 << ph.rb); ++r) {
           uint64_t o = 0;
-          for (int b = 0; b < 3; ++b)
-            if (r >> b & 1) o |= 1ull << ph.fbit[5 + b];
+          for (int b = 0; b < ph.rb; ++b)
+            if (r >> b & 1) o |= 1ull << ph.fbit[kRegBitLo + b];
           dp.params.roff[r] = 16ull * o;
         }
+        dp.rb = ph.rb;
         dp.has_im = ph.has_im;
         dp.hi_bit = ph.hi_bit;
         dp.smem = pass_smem_bytes(ph.L);
-        dp.threads = ph.L >= 13 ? 512 : 256;   // 2^13 tiles: one 512-thread CTA per SM
+        // 2^RB amplitudes per thread; 2^13 tiles run one CTA per SM, smaller ones two
+        dp.threads = (ph.L >= 13 ? 4096 : 2048) >> ph.rb;
         int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
         dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
         pass_partials += dp.grid;
@@ -278,17 +297,11 @@ static int upload(psum_handle_s* h) {
   static bool attr_done_dev[64] = {false};  // function attributes are per device
   bool& attr_done = attr_done_dev[h->device >= 0 && h->device < 64 ? h->device : 0];
   if (!attr_done) {
-    int max_smem = (int)pass_smem_bytes(kMaxTileBits);
-#define SET_SMEM(S, E, I)                                                                              \
-  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  CUDA_TRY(cudaFuncSetAttribute(k_pass<S, E, I, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SET_SMEM(true, true, true) SET_SMEM(true, true, false) SET_SMEM(true, false, true)
-    SET_SMEM(true, false, false) SET_SMEM(false, true, true) SET_SMEM(false, true, false)
-#undef SET_SMEM
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, true, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_pass<false, true, false, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    const int max_smem = (int)pass_smem_bytes(kMaxTileBits);
+    CUDA_TRY(kpass_set_smem_3_256(max_smem));
+    CUDA_TRY(kpass_set_smem_3_512(max_smem));
+    CUDA_TRY(kpass_set_smem_4_128(max_smem));
+    CUDA_TRY(kpass_set_smem_4_256(max_smem));
     attr_done = true;
   }
   h->uploaded = true;
@@ -333,6 +346,12 @@ extern "C" int psum_destroy(psum_handle_t h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_free) cudaEventDestroy(h->ev_free);
+  for (int i = 0; i < psum_handle_s::kBounceSlots; ++i) {
+    if (h->bounce_buf[i]) cudaFreeHost(h->bounce_buf[i]);
+    if (h->bounce_done[i]) cudaEventDestroy(h->bounce_done[i]);
+  }
+  for (auto& ev : h->ex_ev)
+    if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ev_chunk)
     if (ev) cudaEventDestroy(ev);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
@@ -362,11 +381,24 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "plan_tries") {
     if (value < 1 || value > 4096) return fail(PSUM_ERR_INVALID, "plan_tries must be 1..4096");
     h->opt.plan_tries = (int)value;
+  } else if (k == "reg_bits") {
+    if (value != 3 && value != 4) return fail(PSUM_ERR_INVALID, "reg_bits must be 3 or 4");
+    h->opt.reg_bits = (int)value;
   } else if (k == "late_bits") {
     if (value < 0 || value > 8) return fail(PSUM_ERR_INVALID, "late_bits must be 0..8");
     h->opt.late_bits = (int)value;
   } else if (k == "herm_pairing") {
     h->herm_pairing = value ? 1 : 0;
+    return PSUM_OK;
+  } else if (k == "profile_exchange") {
+    h->profile_exchange = value ? 1 : 0;
+    return PSUM_OK;
+  } else if (k == "skip_exchange") {
+    h->skip_exchange = value ? 1 : 0;
+    return PSUM_OK;
+  } else if (k == "copy_threads") {
+    if (value < 0 || value > 256) return fail(PSUM_ERR_INVALID, "copy_threads must be 0..256");
+    h->copy_threads = (int)value;
     return PSUM_OK;
   } else if (k == "lanczos_probe") {
     if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "lanczos_probe must be 0, 1 or 2");
@@ -399,7 +431,8 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
       v[4] += ps.n_remote;
       v[8] += (int64_t)ps.pat_zt.size();
       v[12] += ps.n_flat;
-      v[14] += ps.n_kind_a;
+      v[14] += ps.n_fast;
+      v[15] += (int64_t)ps.bundles.size();
       v[13] += (int64_t)ps.groups.size();
       v[10] = ps.L;
     }
@@ -436,9 +469,9 @@ extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask
 
 // Plan introspection (host only): hands out the device-facing arrays of one pass exactly as the
 // kernels read them, so that the planner can be checked without a device (tests/plan_interpreter.py).
-extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[8], void* groups,
+extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[10], void* groups,
                                 uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
-                                double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64]) {
+                                double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles) {
   if (!h || !counts) return fail(PSUM_ERR_INVALID, "null argument");
   if (!h->planned) PS_TRY(plan(h));
   PartHost* P = find_part(h, g);
@@ -452,7 +485,10 @@ extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[8]
   counts[5] = h->n_loc - ps.L;
   counts[6] = ps.has_im ? 1 : 0;
   counts[7] = ps.hi_bit;
+  counts[8] = (int64_t)ps.bundles.size();
+  counts[9] = ps.rb;
   if (groups) memcpy(groups, ps.groups.data(), ps.groups.size() * sizeof(GroupRec));
+  if (bundles) memcpy(bundles, ps.bundles.data(), ps.bundles.size() * sizeof(BundleRec));
   if (pat_zt) memcpy(pat_zt, ps.pat_zt.data(), ps.pat_zt.size() * sizeof(uint16_t));
   if (pat_inl) memcpy(pat_inl, ps.pat_inl.data(), ps.pat_inl.size() * sizeof(uint16_t));
   if (pat_tptr) memcpy(pat_tptr, ps.pat_tptr.data(), ps.pat_tptr.size() * sizeof(uint32_t));
@@ -497,31 +533,20 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
       const double2* b = bra_is_src ? nullptr : bra;
       if (ex && *pcount + dp.grid > h->partial_cap)
         return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
-#define LAUNCH(S, E, I)                                                                     \
-  do {                                                                                      \
-    if (dp.threads == 512) k_pass<S, E, I, 512><<<dp.grid, 512, dp.smem, st>>>(src, b, y, pp, part); \
-    else k_pass<S, E, I, 256><<<dp.grid, 256, dp.smem, st>>>(src, b, y, pp, part);            \
-  } while (0)
       // Hermitian pairing: expectation only, <psi|H|psi> of a Hermitian operator, local part
       const bool herm = !y && h->hermitian && h->herm_pairing && bra_is_src && D.g == 0;
-#define LAUNCH_H(I)                                                                                     \
-  do {                                                                                                  \
-    if (dp.threads == 512) k_pass<false, true, I, 512, true><<<dp.grid, 512, dp.smem, st>>>(src, b, y, pp, part); \
-    else k_pass<false, true, I, 256, true><<<dp.grid, 256, dp.smem, st>>>(src, b, y, pp, part);           \
-  } while (0)
-      if (dp.has_im) {
-        if (y && ex) LAUNCH(true, true, true);
-        else if (y) LAUNCH(true, false, true);
-        else if (herm) LAUNCH_H(true);
-        else LAUNCH(false, true, true);
-      } else {
-        if (y && ex) LAUNCH(true, true, false);
-        else if (y) LAUNCH(true, false, false);
-        else if (herm) LAUNCH_H(false);
-        else LAUNCH(false, true, false);
-      }
-#undef LAUNCH
-#undef LAUNCH_H
+      const int mode = (y ? kModeStore : 0) | (ex ? kModeExpect : 0) | (dp.has_im ? kModeIm : 0) |
+                       ((herm && ex) ? kModeHerm : 0);
+      cudaError_t le;
+      if (dp.rb == 4)
+        le = dp.threads == 256 ? kpass_launch_4_256(mode, dp.grid, dp.smem, st, src, b, y, pp, part)
+                               : kpass_launch_4_128(mode, dp.grid, dp.smem, st, src, b, y, pp, part);
+      else
+        le = dp.threads == 512 ? kpass_launch_3_512(mode, dp.grid, dp.smem, st, src, b, y, pp, part)
+                               : kpass_launch_3_256(mode, dp.grid, dp.smem, st, src, b, y, pp, part);
+      if (le != cudaSuccess)
+        return fail(PSUM_ERR_CUDA, "k_pass launch (mode %d, rb %d, %d threads) failed: %s", mode, dp.rb, dp.threads,
+                    cudaGetErrorString(le));
       if (ex) *pcount += dp.grid;
     }
   } else {
@@ -583,6 +608,73 @@ extern "C" int psum_expect(psum_handle_t h, const void* psi_dev, double out[2], 
 static int ensure_host_plan(psum_handle_s* h, int late);
 static int host_late_bits(const psum_handle_s* h);
 
+// ---- host -> device copies of caller memory ------------------------------------------------------
+// The reference API hands over a pageable numpy array.  cudaMemcpyAsync from pageable memory is
+// staged by the driver one piece at a time and blocks the calling thread, which would serialise
+// the chunk pipeline; instead host threads copy ahead into a ring of pinned buffers and the DMA
+// engine drains them (one cudaMemcpyAsync per slot).
+static bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int copy_thread_count(const psum_handle_s* h) {
+  if (h->copy_threads > 0) return h->copy_threads;
+  cpu_set_t set;
+  int cores = 8;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+  return std::max(2, std::min(12, cores / std::max(1, h->world)));   // ranks of one node share the cores
+}
+
+static void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
+  const size_t slice = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) {
+    const size_t o = (size_t)t * slice;
+    if (o >= bytes) break;
+    th.emplace_back([=]() { memcpy(dst + o, src + o, std::min(slice, bytes - o)); });
+  }
+  memcpy(dst, src, std::min(slice, bytes));
+  for (auto& t : th) t.join();
+}
+
+// dst_dev[0..bytes) <- src_host (pageable) through the pinned ring, DMA on stream cs
+static int bounce_copy(psum_handle_s* h, const char* src, char* dst, size_t bytes, cudaStream_t cs) {
+  const size_t slot_bytes = (size_t)128 << 20;
+  if (!h->bounce_buf[0]) {
+    for (int i = 0; i < psum_handle_s::kBounceSlots; ++i) {
+      CUDA_TRY(cudaHostAlloc((void**)&h->bounce_buf[i], slot_bytes, cudaHostAllocDefault));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->bounce_done[i], cudaEventDisableTiming));
+    }
+    h->bounce_bytes = slot_bytes;
+  }
+  const int nthreads = copy_thread_count(h);
+  for (size_t off = 0; off < bytes; off += slot_bytes) {
+    const size_t nb = std::min(slot_bytes, bytes - off);
+    const int s = h->bounce_next;
+    h->bounce_next = (s + 1) % psum_handle_s::kBounceSlots;
+    CUDA_TRY(cudaEventSynchronize(h->bounce_done[s]));   // the DMA that last read this slot is done
+    parallel_memcpy(h->bounce_buf[s], src + off, nb, nthreads);
+    CUDA_TRY(cudaMemcpyAsync(dst + off, h->bounce_buf[s], nb, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(h->bounce_done[s], cs));
+  }
+  return PSUM_OK;
+}
+
+// Once copies FROM the caller's host buffer are queued, an error return must not leave them in
+// flight (the caller may free the buffer): the guard drains the copy stream unless disarmed.
+struct CopyGuard {
+  cudaStream_t cs = nullptr;
+  ~CopyGuard() {
+    if (cs) cudaStreamSynchronize(cs);
+  }
+};
+
 // <psi|H|psi> for a state that lives in HOST memory: the H2D copy is cut into 2^late_bits chunks
 // on a copy stream and every "early" pass (hi_bit inside a chunk) runs chunk by chunk as the data
 // arrives; only the passes that combine different chunks wait for the whole state.
@@ -613,19 +705,22 @@ extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi
   CUDA_TRY(cudaEventRecord(h->ev_free, st));
   CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
   const size_t cbytes = bytes >> late;
-  for (uint64_t k = 0; k < nchunks; ++k) {
-    CUDA_TRY(cudaMemcpyAsync((char*)psi_dev + k * cbytes, (const char*)psi_host + k * cbytes, cbytes,
-                             cudaMemcpyHostToDevice, h->copy_stream));
-    CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
-  }
   if (h->dparts_h.size() != 1) return fail(PSUM_ERR_INVALID, "unexpected plan shape");
   const DevPart& D = h->dparts_h[0];
   const int cbits = h->n_loc - late;
   size_t n_early = 0;  // early passes come first in the plan (stage 1 of choose_passes)
   while (n_early < D.passes.size() && D.passes[n_early].hi_bit < cbits) ++n_early;
   const double2* psi = (const double2*)psi_dev;
+  const bool pageable = host_is_pageable(psi_host);
   size_t pcount = 0;
+  CopyGuard guard;
+  guard.cs = h->copy_stream;
   for (uint64_t k = 0; k < nchunks; ++k) {
+    char* dst = (char*)psi_dev + k * cbytes;
+    const char* srcp = (const char*)psi_host + k * cbytes;
+    if (pageable) PS_TRY(bounce_copy(h, srcp, dst, cbytes, h->copy_stream));
+    else CUDA_TRY(cudaMemcpyAsync(dst, srcp, cbytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
     if (n_early) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, 0, n_early, k, nchunks));
   }
@@ -633,7 +728,9 @@ extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi
     PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, n_early, D.passes.size()));
   k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
   CUDA_TRY(cudaGetLastError());
-  return fetch_scalars(h, 1, out, st);
+  PS_TRY(fetch_scalars(h, 1, out, st));   // st waited for every chunk: the copies are complete
+  guard.cs = nullptr;
+  return PSUM_OK;
 }
 
 extern "C" int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, double out[2],
@@ -996,6 +1093,7 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     else remote.push_back(&D);
   }
   size_t n_early = 0;
+  CopyGuard guard;
   if (host_src) {
     // ---- chunked H2D + the chunk-local passes of the local part -------------------------------
     if (!h->copy_stream) {
@@ -1008,15 +1106,17 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     CUDA_TRY(cudaEventRecord(h->ev_free, st));
     CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
     const size_t cbytes = (N * sizeof(double2)) >> late;
-    for (uint64_t k = 0; k < nchunks; ++k) {
-      CUDA_TRY(cudaMemcpyAsync((char*)psi_dev + k * cbytes, (const char*)host_src + k * cbytes, cbytes,
-                               cudaMemcpyHostToDevice, h->copy_stream));
-      CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
-    }
     const int cbits = h->n_loc - late;
     if (local && late > 0)
       while (n_early < local->passes.size() && local->passes[n_early].hi_bit < cbits) ++n_early;
+    const bool pageable = host_is_pageable(host_src);
+    guard.cs = h->copy_stream;
     for (uint64_t k = 0; k < nchunks; ++k) {
+      char* dst = (char*)psi_dev + k * cbytes;
+      const char* srcp = (const char*)host_src + k * cbytes;
+      if (pageable) PS_TRY(bounce_copy(h, srcp, dst, cbytes, h->copy_stream));
+      else CUDA_TRY(cudaMemcpyAsync(dst, srcp, cbytes, cudaMemcpyHostToDevice, h->copy_stream));
+      CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
       CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
       if (n_early)
         PS_TRY(run_part(h, *local, psi, psi, nullptr, 0, true, remote.empty() && n_early == local->passes.size(),
@@ -1031,14 +1131,29 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     if (must_wait_used) CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_used[s], 0));
     double2* buf = (double2*)recv_dev + (uint64_t)s * N;
     const int peer = h->rank ^ D->g;
-    NCCL_TRY(g_nccl.GroupStart());
-    NCCL_TRY(g_nccl.Send(psi, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
-    NCCL_TRY(g_nccl.Recv(buf, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
-    NCCL_TRY(g_nccl.GroupEnd());
+    if (h->profile_exchange) {
+      while (h->ex_ev.size() < (size_t)(2 * (h->ex_count + 1))) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreate(&ev));
+        h->ex_ev.push_back(ev);
+      }
+      CUDA_TRY(cudaEventRecord(h->ex_ev[2 * h->ex_count], h->comm_stream));
+    }
+    if (!h->skip_exchange) {
+      NCCL_TRY(g_nccl.GroupStart());
+      NCCL_TRY(g_nccl.Send(psi, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
+      NCCL_TRY(g_nccl.Recv(buf, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
+      NCCL_TRY(g_nccl.GroupEnd());
+    }
+    if (h->profile_exchange) {
+      CUDA_TRY(cudaEventRecord(h->ex_ev[2 * h->ex_count + 1], h->comm_stream));
+      ++h->ex_count;
+    }
     CUDA_TRY(cudaEventRecord(h->ev_recv[s], h->comm_stream));
     return PSUM_OK;
   };
   size_t posted = 0;
+  h->ex_count = 0;
   for (; posted < remote.size() && posted < (size_t)nbuf; ++posted)
     PS_TRY(post_exchange(remote[posted], (int)(posted % nbuf), false));
   // (rest of the) local part: overlaps the exchanges posted above
@@ -1065,7 +1180,31 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     CUDA_TRY(cudaGetLastError());
     if (h->comm) NCCL_TRY(g_nccl.AllReduce(h->d_scalar, h->d_scalar, 2, kNcclFloat64, kNcclSum, h->comm, st));
     PS_TRY(fetch_scalars(h, 1, expect_out, st));
+    guard.cs = nullptr;   // st waited for every chunk and is drained: the host copies are complete
   }
+  if (h->profile_exchange && h->ex_count > 0) {
+    // per-exchange durations on the communication stream (the stream is serial, so their sum is
+    // its busy time) and the span from the first post to the last arrival
+    CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+    double sum = 0.0;
+    for (int i = 0; i < h->ex_count; ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->ex_ev[2 * i], h->ex_ev[2 * i + 1]));
+      sum += ms;
+    }
+    float span = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&span, h->ex_ev[0], h->ex_ev[2 * h->ex_count - 1]));
+    h->ex_stats[0] = h->ex_count;
+    h->ex_stats[1] = (double)(N * sizeof(double2));
+    h->ex_stats[2] = sum;
+    h->ex_stats[3] = span;
+  }
+  return PSUM_OK;
+}
+
+extern "C" int psum_exchange_stats(psum_handle_t h, double out[4]) {
+  if (!h || !out) return fail(PSUM_ERR_INVALID, "null argument");
+  for (int i = 0; i < 4; ++i) out[i] = h->ex_stats[i];
   return PSUM_OK;
 }
 

@@ -9,11 +9,14 @@
 // Signs are never evaluated per (term, amplitude):
 //   * bits outside S:   folded into the coefficient once per (tile, term)      ("fold")
 //   * equal in-tile z-patterns of one group are merged into one pattern          ("compaction")
-//   * tile bits 5..7 (the 8 amplitudes a thread owns, chosen by the planner among the free
-//     qubits the pass's z-masks touch least): patterns are summed per class zr = (zt >> 5) & 7
-//     and added with compile-time signs; a group whose patterns are all class 0 ("flat") has
-//     one D for the 8 amplitudes                                                ("class sums")
+//   * register bits = tile bits 5..5+RB-1 (the 2^RB amplitudes a thread owns): patterns are summed
+//     per class zr = (zt >> 5) & (2^RB - 1) and added with compile-time signs; a group whose
+//     patterns are all class 0 ("flat") has one D for all amplitudes of a thread   ("class sums")
 //   * the remaining tile bits: one popc per (pattern, thread)
+// Partner sharing: x-groups whose masks differ only in register bits form a bundle; the 2^RB
+// partner amplitudes are loaded ONCE per bundle and every member applies its own compile-time
+// register permutation pv[r ^ xr] -- the shared-memory pipe, which bounds this kernel, sees one
+// load set per bundle instead of one per group.
 // Kernel A (k_stream) is the plain streaming form used for n_loc < 11 qubits.
 #pragma once
 #include <cuda_runtime.h>
@@ -23,11 +26,10 @@
 
 namespace psum {
 
-constexpr int kThreads = 256;
-constexpr int kAmpsPerThread = 8;
-constexpr int kRoundAmps = kThreads * kAmpsPerThread;  // 2048
+constexpr int kThreads = 256;   // block size of the small vector kernels
 
 struct PassParams {
+  const BundleRec* bundles;
   const GroupRec* groups;
   const uint16_t* pat_zt;
   const uint16_t* pat_inl;
@@ -41,10 +43,16 @@ struct PassParams {
   int accumulate;
   uint64_t ntiles;
   uint64_t tile_begin, tile_end;  // tile range of this launch (whole pass: 0 .. ntiles)
-  uint64_t roff[8];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
-  uint8_t fbit[16];  // qubit of tile bit j (0..4 lane, 5..7 register, 8.. warp/round)
-  uint8_t nbit[64];  // positions of the non-free local bits, ascending
+  uint64_t roff[16];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
+  uint8_t fbit[16];   // qubit of tile bit j (0..4 lane, 5..5+RB-1 register, then warp/round)
+  uint8_t nbit[64];   // positions of the non-free local bits, ascending
 };
+
+// shared memory of one k_pass CTA (bytes), L tile bits
+__host__ __device__ constexpr size_t pass_smem_bytes_c(int L) {
+  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 64 + sizeof(GroupRec) * (kGrpChunk + 1) +
+         sizeof(BundleRec) * (kGrpChunk + 1) + 16 * 16 + 8 * 9 * 64;
+}
 
 __device__ __forceinline__ double flip_sign(double v, int s) {
   return __hiloint2double(__double2hiint(v) ^ (s << 31), __double2loint(v));
@@ -84,14 +92,69 @@ __device__ __forceinline__ double2 block_reduce(double2 v, double2* scratch) {
 // ------------------------------------------------------------------------------------------
 // Kernel B: one pass over all tiles of a free set.
 // ------------------------------------------------------------------------------------------
-// D[(C >> 3) * 8 + r] += (-1)^{popc(r & C)} s  for r = 0..7, with C a compile-time class
-#define PSUM_CLASS_CASE(C)                                       \
-  case C: {                                                      \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) {              \
-      if (__popc(r & ((C) & 7)) & 1) D[((C) >> 3) * 8 + r] -= s; \
-      else D[((C) >> 3) * 8 + r] += s;                           \
-    }                                                            \
-  } break;
+#define PSUM_REP32(M)                                                                        \
+  M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15)      \
+  M(16) M(17) M(18) M(19) M(20) M(21) M(22) M(23) M(24) M(25) M(26) M(27) M(28) M(29) M(30) M(31)
+
+// D[(C / NA) * NA + r] += (-1)^{popc(r & C)} s  for r = 0..NA-1, C a compile-time class (im*NA + zr)
+template <int NA, int C, int ND>
+__device__ __forceinline__ void add_class(double (&D)[ND], double s) {
+  if constexpr (C < ND) {
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      if (__popc(r & (C & (NA - 1))) & 1) D[(C / NA) * NA + r] -= s;
+      else D[(C / NA) * NA + r] += s;
+    }
+  }
+}
+
+// fast variants: yacc[r] += d_r * pv[r ^ XR] with d_r = dp, or dm where popc(r & XR) is odd (V >= NA)
+template <int NA, int V>
+__device__ __forceinline__ void fast_fma(double2 (&yacc)[NA], const double2 (&pv)[NA], double dp, double dm) {
+  if constexpr (V < 2 * NA) {
+    constexpr int XR = V & (NA - 1);
+    constexpr bool SGN = V >= NA;
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      const double d = (SGN && (__popc(r & XR) & 1)) ? dm : dp;
+      yacc[r].x = fma(d, pv[r ^ XR].x, yacc[r].x);
+      yacc[r].y = fma(d, pv[r ^ XR].y, yacc[r].y);
+    }
+  }
+}
+
+// the same with an imaginary slot 1: yacc[r] += (s0 + i d_r) * pv[r ^ XR], d_r = +-s1
+template <int NA, int V>
+__device__ __forceinline__ void fast_fma_im(double2 (&yacc)[NA], const double2 (&pv)[NA], double s0, double s1) {
+  if constexpr (V < 2 * NA) {
+    constexpr int XR = V & (NA - 1);
+    constexpr bool SGN = V >= NA;
+    const double n1 = -s1;
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      const bool neg = SGN && (__popc(r & XR) & 1);
+      yacc[r].x = fma(s0, pv[r ^ XR].x, fma(neg ? s1 : n1, pv[r ^ XR].y, yacc[r].x));
+      yacc[r].y = fma(s0, pv[r ^ XR].y, fma(neg ? n1 : s1, pv[r ^ XR].x, yacc[r].y));
+    }
+  }
+}
+
+// general members: yacc[r] += (D[r] + i D[NA + r]) * pv[r ^ XR]
+template <int NA, int XR, bool CPLX, int ND>
+__device__ __forceinline__ void perm_fma(double2 (&yacc)[NA], const double2 (&pv)[NA], const double (&D)[ND]) {
+  if constexpr (XR < NA) {
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      if constexpr (CPLX) {
+        yacc[r].x = fma(D[r], pv[r ^ XR].x, fma(-D[NA + r], pv[r ^ XR].y, yacc[r].x));
+        yacc[r].y = fma(D[r], pv[r ^ XR].y, fma(D[NA + r], pv[r ^ XR].x, yacc[r].y));
+      } else {
+        yacc[r].x = fma(D[r], pv[r ^ XR].x, yacc[r].x);
+        yacc[r].y = fma(D[r], pv[r ^ XR].y, yacc[r].y);
+      }
+    }
+  }
+}
 
 // sum of the (tile-folded, thread-signed) coefficients of `cnt` patterns starting at p
 __device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, int& p, int cnt, uint32_t t0) {
@@ -110,46 +173,43 @@ __device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, in
 //                          launch only);  no-STORE mode -> sum conj(bra_i) * contribution_i
 //   IM    : the pass has imaginary component patterns (complex D); real-only passes carry half
 //           the class accumulators
+//   RB,NT : 2^RB amplitudes per thread, NT threads per CTA.  (3,256) and (4,128): two CTAs per SM,
+//           tiles up to 2^12;  (3,512) and (4,256): one CTA per SM, 2^13 tiles
 //   bra == nullptr -> the bra is the staged tile itself (<psi|H|psi> on the local part)
-#ifndef PSUM_LOOPA_UNROLL
-#define PSUM_LOOPA_UNROLL 2
-#endif
-constexpr int kLoopAUnroll = PSUM_LOOPA_UNROLL;
-#ifndef PSUM_MIN_CTAS
-#define PSUM_MIN_CTAS 2
-#endif
-// NT = threads per CTA: 256 (two CTAs per SM, tiles up to 2^12) or 512 (one CTA per SM, 2^13 tiles)
-//   HERM  : (expectation only, Hermitian H, bra == source) a local off-diagonal group whose x has
+//   HERM  : (expectation only, Hermitian H, bra == source) a local off-diagonal bundle whose x has
 //           its highest tile bit among the warp-uniform bits is evaluated only on the half of the
 //           amplitudes with that bit clear, with doubled coefficients: the pair (i, i^x)
 //           contributes z + conj(z) = 2 Re z.  The imaginary part (identically zero for a
 //           Hermitian operator) is returned as exactly 0.
-template <bool STORE, bool EXPECT, bool IM, int NT, bool HERM = false>
-__global__ void __launch_bounds__(NT, NT == 256 ? (IM ? 2 : PSUM_MIN_CTAS) : 1)
+template <bool STORE, bool EXPECT, bool IM, int RB, int NT, bool HERM = false>
+__global__ void __launch_bounds__(NT, (NT << RB) <= 2048 ? 2 : 1)
 k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2* __restrict__ y,
        const PassParams P, double2* __restrict__ partial) {
+  constexpr int NA = 1 << RB;
+  constexpr int ND = IM ? 2 * NA : NA;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = P.L;
   const uint32_t tile_amps = 1u << L;
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   PatRec* pat = reinterpret_cast<PatRec*>(tile + tile_amps);
   uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
-  uint4* grp4 = reinterpret_cast<uint4*>(offHi + 32);               // 3 x uint4 per group record
-  double2* red = reinterpret_cast<double2*>(grp4 + 3 * (kGrpChunk + 1));
+  uint4* grp4 = reinterpret_cast<uint4*>(offHi + 64);               // 3 x uint4 per group record
+  uint4* bun4 = grp4 + 3 * (kGrpChunk + 1);                         // 1 x uint4 per bundle record
+  double2* red = reinterpret_cast<double2*>(bun4 + (kGrpChunk + 1));
   uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // deposit tables: offset of tile element e = offLo8[e & 255] | offHi[e >> 8]
-  uint64_t offLo8 = 0;
+  // deposit tables: offset of tile element e = offLo[e & 127] | offHi[e >> 7]
+  uint64_t offLo = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) offLo8 |= (uint64_t)((tid >> j) & 1) << P.fbit[j];
-  const uint64_t offLane = offLo8 & ((1ull << P.fbit[0]) | (1ull << P.fbit[1]) | (1ull << P.fbit[2]) |
-                                     (1ull << P.fbit[3]) | (1ull << P.fbit[4]));
-  if (tid < 32) {
+  for (int j = 0; j < 7; ++j) offLo |= (uint64_t)((tid >> j) & 1) << P.fbit[j];
+  const uint64_t offLane = offLo & ((1ull << P.fbit[0]) | (1ull << P.fbit[1]) | (1ull << P.fbit[2]) |
+                                    (1ull << P.fbit[3]) | (1ull << P.fbit[4]));
+  if (tid < 64) {
     uint64_t o = 0;
-    for (int j = 8; j < L; ++j) o |= (uint64_t)((tid >> (j - 8)) & 1) << P.fbit[j];
+    for (int j = 7; j < L; ++j) o |= (uint64_t)((tid >> (j - 7)) & 1) << P.fbit[j];
     offHi[tid] = o;
   }
   // tile id -> base index: 6 bits of the tile id per table lookup
@@ -161,21 +221,20 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     baseT[e] = o;
   }
   __syncthreads();
-  const uint64_t b5 = 1ull << P.fbit[5], b6 = 1ull << P.fbit[6], b7 = 1ull << P.fbit[7];
-  const int nrounds = (int)(tile_amps / (NT * 8));
+  const int nrounds = (int)(tile_amps / (NT * NA));
   const int nload = (int)(tile_amps / NT);
   const bool one_chunk = (P.nchunks == 1);
 
   double2 eacc = make_double2(0.0, 0.0);
 
-  // Stage a chunk: copy its group records to shared memory, then fold -- bits outside the free
-  // set become a per-tile sign of each term; equal in-tile patterns of a group are summed into
-  // one coefficient, stored in pat[] and (first two patterns of a group) inline in its record.
+  // Stage a chunk: copy its bundle and group records to shared memory, then fold -- bits outside
+  // the free set become a per-tile sign of each term; equal in-tile patterns of a group are summed
+  // into one coefficient, stored in pat[] and (first two patterns of a group) inline in its record.
   auto stage_chunk = [&](const ChunkRec ch, uint64_t base) {
-    const int ng = ch.ng & 0xffff;
-    for (int g = tid; g < ng * 3; g += NT)
+    for (int g = tid; g < ch.ng * 3; g += NT)
       grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
-    if (tid < 3) grp4[ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);  // prefetch overrun record
+    for (int b = tid; b < ch.nb; b += NT)
+      bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch.b0)[b];
     __syncthreads();
     for (int p = tid; p < ch.np; p += NT) {
       const int gp = ch.p0 + p;
@@ -203,8 +262,9 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 
     __syncthreads();  // previous tile fully consumed
     for (int j = 0; j < nload; ++j) {
-      const uint64_t idx = base | offLo8 | offHi[(j * NT + tid) >> 8];
-      cp_async16(&tile[j * NT + tid], &src[idx]);
+      const int e = j * NT + tid;
+      const uint64_t idx = base | offLo | offHi[e >> 7];
+      cp_async16(&tile[e], &src[idx]);
       // the old y of this tile is needed when the rounds start: pull its lines into L2 now
       // (one prefetch per 128-byte line: 8 amplitudes)
       if (STORE && P.accumulate && (tid & 7) == 0)
@@ -215,12 +275,12 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     __syncthreads();
 
     for (int rnd = 0; rnd < nrounds; ++rnd) {
-      const uint32_t t0 = (uint32_t)rnd * (NT * 8) + (uint32_t)warp * 256u + (uint32_t)lane;
-      const uint64_t i0 = base | offLane | offHi[t0 >> 8];
-      double2 yacc[8];
+      const uint32_t t0 = (uint32_t)rnd * (NT * NA) + (uint32_t)warp * (32u * NA) + (uint32_t)lane;
+      const uint64_t i0 = base | offLane | offHi[t0 >> 7];   // register bits of t0 are clear
+      double2 yacc[NA];
       const char* ybase = reinterpret_cast<const char*>(y + i0);
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < NA; ++r)
         yacc[r] = (STORE && P.accumulate) ? *reinterpret_cast<const double2*>(ybase + P.roff[r])
                                           : make_double2(0.0, 0.0);
 
@@ -231,125 +291,97 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           stage_chunk(ch, base);
           __syncthreads();
         }
-        const int ng = ch.ng & 0xffff, ng_a = ch.ng >> 16;
-
-        // ---- loop A: local real groups with <= 2 patterns (slot 0 class 0, slot 1 class c1), sorted
-        // by c1 so that each class runs its own branch-free loop with compile-time signs ----------
-        {
-          int g = 0;
-          const uint64_t acnt_re = reinterpret_cast<const uint64_t*>(ch.a_cnt)[0];
-          const uint64_t acnt_im = reinterpret_cast<const uint64_t*>(ch.a_cnt)[1];
+        for (int b = 0; b < ch.nb; ++b) {
+          const uint4 B = bun4[b];
+          if (HERM) {  // partner half of a paired bundle (warp-uniform)
+            const uint32_t hb = (B.y >> 8) & 0xffu;
+            if (hb && ((t0 >> (hb - 1u)) & 1u)) continue;
+          }
+          // one set of partner amplitudes for every member of the bundle
+          double2 pv[NA];
+          if (!(B.x >> 31)) {
+            const double2* pp = tile + (t0 ^ B.x);   // register bits clear on both sides
 #pragma unroll
-          for (int cls = 0; cls < (IM ? 16 : 8); ++cls) {
-            const int gend = g + (int)(((cls < 8 ? acnt_re : acnt_im) >> (8 * (cls & 7))) & 0xffull);
-#pragma unroll(kLoopAUnroll)
-            for (; g < gend; ++g) {
-              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
-              if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
-              const uint32_t tp = t0 ^ h0.x;
-              double2 pv[8];
+            for (int r = 0; r < NA; ++r) pv[r] = pp[r << 5];
+          } else {
+            const char* pp = reinterpret_cast<const char*>(src + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
 #pragma unroll
-              for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
+            for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
+          }
+          int g = (int)(B.y >> 16);
+          const int gend = g + (int)(B.y & 0xffu);
+          for (; g < gend; ++g) {
+            const uint4 h0 = grp4[3 * g];
+            const uint32_t var = (h0.y >> 22) & 63u;
+            if (var < 2u * NA) {
+              // fast member: <= 2 patterns, coefficients inline in the record
+              const uint4 hc = grp4[3 * g + 1];
               const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
               const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
-              if (cls == 0) {  // flat: slot 1 (if any) is real class 0 too
-                const double d = s0 + s1;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                  yacc[r].x = fma(d, pv[r].x, yacc[r].x);
-                  yacc[r].y = fma(d, pv[r].y, yacc[r].y);
+              if (IM && ((h0.y >> 19) & 1u)) {
+                switch (var) {
+#define PSUM_FAST_CASE(V) case V: fast_fma_im<NA, V>(yacc, pv, s0, s1); break;
+                  PSUM_REP32(PSUM_FAST_CASE)
+#undef PSUM_FAST_CASE
                 }
-              } else if (cls < 8) {
-                const double dp = s0 + s1, dm = s0 - s1;
+                continue;
+              }
+              const double dp = s0 + s1, dm = s0 - s1;
+              switch (var) {
+#define PSUM_FAST_CASE(V) case V: fast_fma<NA, V>(yacc, pv, dp, dm); break;
+                PSUM_REP32(PSUM_FAST_CASE)
+#undef PSUM_FAST_CASE
+              }
+              continue;
+            }
+            // general member: class entry lists
+            const uint4 h2 = grp4[3 * g + 2];
+            const uint32_t xr = (h0.x >> 5) & (uint32_t)(NA - 1);
+            int p = (int)(h0.y & 0xffffu);
+            if ((h0.y >> 21) & 1u) {
+              // flat: one real class-0 entry -> the same D for all amplitudes of the thread
+              const double s = pattern_sum(pat4, p, (int)(h2.z & 0x7ffu), t0);
+              switch (xr) {
+#define PSUM_FLAT_CASE(V) case V: fast_fma<NA, (V < NA ? V : 0)>(yacc, pv, s, s); break;
+                PSUM_REP32(PSUM_FLAT_CASE)
+#undef PSUM_FLAT_CASE
+              }
+              continue;
+            }
+            const int nent = (int)((h0.y >> 16) & 7u);
+            uint64_t ents = (uint64_t)h2.z | ((uint64_t)h2.w << 32);
+            double D[ND];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                  const double d = (__popc(r & cls) & 1) ? dm : dp;
-                  yacc[r].x = fma(d, pv[r].x, yacc[r].x);
-                  yacc[r].y = fma(d, pv[r].y, yacc[r].y);
-                }
-              } else {  // slot 1 is imaginary: D = s0 + i (+-s1)
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                  const double di = (__popc(r & (cls & 7)) & 1) ? -s1 : s1;
-                  yacc[r].x = fma(s0, pv[r].x, fma(-di, pv[r].y, yacc[r].x));
-                  yacc[r].y = fma(s0, pv[r].y, fma(di, pv[r].x, yacc[r].y));
-                }
+            for (int r = 0; r < ND; ++r) D[r] = 0.0;
+            for (int e = 0; e < nent; ++e) {
+              const uint32_t ent = (uint32_t)ents & 0xffffu;
+              ents >>= 16;
+              const double s = pattern_sum(pat4, p, (int)(ent & 0x7ffu), t0);
+              switch (ent >> 11) {
+#define PSUM_CLASS_CASE(C) case C: add_class<NA, C, ND>(D, s); break;
+                PSUM_REP32(PSUM_CLASS_CASE)
+#undef PSUM_CLASS_CASE
               }
             }
-          }
-        }
-
-        // ---- loop B: everything else ------------------------------------------------------------
-        for (int g = ng_a; g < ng; ++g) {
-          const uint4 h0 = grp4[3 * g];
-          if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
-          const uint4 h2 = grp4[3 * g + 2];
-          const uint32_t xt = h0.x & 0x7fffffffu;
-          const bool remote = (h0.x >> 31) != 0;
-          int p = (int)(h0.y & 0xffffu);
-          double2 pv[8];
-          if (!remote) {
-            const uint32_t tp = t0 ^ xt;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) pv[r] = tile[tp ^ ((uint32_t)r << 5)];
-          } else {
-            const uint64_t ip = i0 ^ ((uint64_t)h2.x | ((uint64_t)h2.y << 32));
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-              pv[r] = __ldg(&src[ip ^ ((r & 1) ? b5 : 0ull) ^ ((r & 2) ? b6 : 0ull) ^
-                                 ((r & 4) ? b7 : 0ull)]);
-          }
-          if ((h0.y >> 21) & 1u) {
-            // flat group: one real class-0 entry -> the same D for the 8 amplitudes
-            const double s = pattern_sum(pat4, p, (int)(h2.z & 0xfffu), t0);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              yacc[r].x = fma(s, pv[r].x, yacc[r].x);
-              yacc[r].y = fma(s, pv[r].y, yacc[r].y);
-            }
-            continue;
-          }
-          const int nent = (int)((h0.y >> 16) & 7u);
-          uint64_t ents = (uint64_t)h2.z | ((uint64_t)h2.w << 32);
-          double D[IM ? 16 : 8];
-#pragma unroll
-          for (int r = 0; r < (IM ? 16 : 8); ++r) D[r] = 0.0;
-          for (int e = 0; e < nent; ++e) {
-            const uint32_t ent = (uint32_t)ents & 0xffffu;
-            ents >>= 16;
-            const double s = pattern_sum(pat4, p, (int)(ent & 0xfffu), t0);
-            if (IM) {
-              switch (ent >> 12) {
-                PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
-                PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
-                PSUM_CLASS_CASE(8) PSUM_CLASS_CASE(9) PSUM_CLASS_CASE(10) PSUM_CLASS_CASE(11)
-                PSUM_CLASS_CASE(12) PSUM_CLASS_CASE(13) PSUM_CLASS_CASE(14) PSUM_CLASS_CASE(15)
+            if (IM && ((h0.y >> 20) & 1u)) {
+              switch (xr) {
+#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, IM, ND>(yacc, pv, D); break;
+                PSUM_REP32(PSUM_PERM_CASE)
+#undef PSUM_PERM_CASE
               }
             } else {
-              switch (ent >> 12) {
-                PSUM_CLASS_CASE(0) PSUM_CLASS_CASE(1) PSUM_CLASS_CASE(2) PSUM_CLASS_CASE(3)
-                PSUM_CLASS_CASE(4) PSUM_CLASS_CASE(5) PSUM_CLASS_CASE(6) PSUM_CLASS_CASE(7)
+              switch (xr) {
+#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, false, ND>(yacc, pv, D); break;
+                PSUM_REP32(PSUM_PERM_CASE)
+#undef PSUM_PERM_CASE
               }
-            }
-          }
-          if (IM && ((h0.y >> 20) & 1u)) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              yacc[r].x = fma(D[r], pv[r].x, fma(-D[(IM ? 8 : 0) + r], pv[r].y, yacc[r].x));
-              yacc[r].y = fma(D[r], pv[r].y, fma(D[(IM ? 8 : 0) + r], pv[r].x, yacc[r].y));
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              yacc[r].x = fma(D[r], pv[r].x, yacc[r].x);
-              yacc[r].y = fma(D[r], pv[r].y, yacc[r].y);
             }
           }
         }
       }
       // epilogue of the round: y and/or the expectation partial
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < NA; ++r) {
         if (EXPECT) {
           const double2 b = bra ? __ldg(reinterpret_cast<const double2*>(
                                       reinterpret_cast<const char*>(bra + i0) + P.roff[r]))
@@ -368,8 +400,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     if (tid == 0) partial[blockIdx.x] = tot;
   }
 }
-#undef PSUM_CLASS_CASE
 
+#ifdef PSUM_SMALL_KERNELS   // defined by psum.cu only: the kernels below are not templates
 // ------------------------------------------------------------------------------------------
 // Kernel A: streaming form, one amplitude per thread (grid-stride).  Any n_loc >= 0.
 // ------------------------------------------------------------------------------------------
@@ -658,5 +690,7 @@ k_argmin_after(const double* __restrict__ d, uint64_t n_amps, ValIdx lo, int hav
     partial[blockIdx.x] = best;
   }
 }
+
+#endif  // PSUM_SMALL_KERNELS
 
 }  // namespace psum

@@ -40,19 +40,35 @@ struct CompTerm {  // real-valued component term of one shard/part: value * (im 
 };
 
 // ---- device-facing records (layout shared with the kernels) --------------------------------
+// A pass keeps 2^RB amplitudes per thread in registers (RB = 3 or 4 "register bits" = tile bits
+// 5 .. 5+RB-1).  x-groups of a pass whose masks differ only in register bits form a BUNDLE: the
+// 2^RB partner amplitudes a thread needs are the same set for every member (the register part of
+// the mask is a permutation inside the thread), so a bundle costs ONE set of partner loads.
+struct BundleRec {    // 16 bytes
+  uint32_t xo;        // tile-local xor with the register bits cleared; bit31 = remote flag
+  uint32_t meta;      // bits 0..7 member count, bits 8..15 hbit, bits 16..31 first member (group
+                      // index inside the chunk).  hbit = 1 + tile bit (warp-uniform, i.e. >= 5+RB)
+                      // of the highest set bit of xo for local bundles, else 0: the Hermitian
+                      // <psi|H|psi> kernels process such a bundle only for amplitudes with that bit
+                      // clear and double it (pair i, i^x)
+  uint64_t xlo;       // local x mask with the register QUBITS cleared (partner base of remote bundles)
+};
+static_assert(sizeof(BundleRec) == 16, "BundleRec layout");
+
 struct GroupRec {     // 48 bytes
   uint32_t xt;        // tile-local xor (x gathered onto the tile index); bit31 = remote flag
   uint32_t meta;      // bits 0..15 first pattern (relative to the chunk), 16..18 entry count,
+                      // bit 19 = slot 1 of a fast group is imaginary,
                       // bit 20 = has imaginary patterns, bit 21 = flat (one real class-0 entry),
-                      // bits 24..27 = class (im*8 + zr) of the inline pattern in slot 1 (kind A groups)
-                      // bits 28..31 = hbit: 1 + tile bit (>= 8, i.e. warp-uniform) of the highest
-                      //               set bit of xt for local off-diagonal groups, else 0.  The
-                      //               Hermitian <psi|H|psi> kernels process such a group only for
-                      //               amplitudes with that bit clear and double it (pair i, i^x)
+                      // bits 22..27 = variant: v < NA      fast, slot-1 class 0,  xr = v
+                      //                        NA <= v < 2NA fast, slot-1 class = xr = v - NA
+                      //                        63          general (class entry lists)
+                      //   (xr = register bits of xt; "fast" = <= 2 patterns, slot 0 real class 0)
+                      // bits 28..31 = hbit of the group's bundle (kept for the plan checker)
   uint32_t zt0, zt1;  // in-tile z-patterns of the first two patterns (inline copy)
   double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
-  uint16_t ent[4];    // non-empty classes: (cls << 12) | count ; cls = im*8 + ((zt >> 5) & 7)
+  uint16_t ent[4];    // non-empty classes: (cls << 11) | count ; cls = im*NA + ((zt >> 5) & (NA-1))
 };
 static_assert(sizeof(GroupRec) == 48, "GroupRec layout");
 
@@ -64,16 +80,16 @@ struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is writ
 
 struct ChunkRec {  // 32 bytes
   int32_t g0;  // first group
-  int32_t ng;  // low 16 bits: groups in the chunk; high 16 bits: how many of them (the first
-               // ones) are "kind A": local, real, <= 2 patterns with slot 0 of class 0 -> fast loop
+  int32_t ng;  // groups in the chunk
   int32_t p0, np;
-  uint8_t a_cnt[16];  // kind A groups are sorted by the class of slot 1 (0..7 real, 8..15
-                      // imaginary): count per class
+  int32_t b0, nb;  // bundles of the chunk (members are consecutive groups, in bundle order)
+  int32_t pad[2];
 };
 static_assert(sizeof(ChunkRec) == 32, "ChunkRec layout");
 
 constexpr int kMaxTileBits = 13;
-constexpr int kRegBitLo = 5;     // tile bits 5..7 live in registers (8 amplitudes per thread)
+constexpr int kRegBitLo = 5;     // tile bits 5 .. 5+RB-1 live in registers (2^RB amplitudes per thread)
+constexpr int kVarGeneral = 63;
 #ifndef PSUM_PAT_CHUNK
 #define PSUM_PAT_CHUNK 1024
 #endif
@@ -85,12 +101,14 @@ constexpr int kGrpChunk = PSUM_GRP_CHUNK;  // groups staged in shared memory at 
 
 struct PassHost {
   int L = 0;                   // tile bits
+  int rb = 3;                  // register bits (2^rb amplitudes per thread)
   uint64_t free_mask = 0;      // over local qubits
-  uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..7 register bits, 8.. warp/round
+  uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..5+rb-1 register bits, then warp/round
   bool has_im = false;         // any imaginary component pattern in this pass
   int hi_bit = 0;              // highest local qubit the pass combines (free set or any member x-mask)
-  int64_t n_flat = 0;          // groups whose D is the same for the 8 register amplitudes
-  int64_t n_kind_a = 0;        // of those: local, <= 2 patterns (fast loop)
+  int64_t n_flat = 0;          // groups whose D is the same for all register amplitudes
+  int64_t n_fast = 0;          // groups served by a fast variant (real, <= 2 inline patterns)
+  std::vector<BundleRec> bundles;
   std::vector<GroupRec> groups;
   std::vector<uint16_t> pat_zt;
   std::vector<uint16_t> pat_inl;   // (group index in chunk) * 2 + slot for inlined patterns, else 0xffff
@@ -125,6 +143,7 @@ struct PlanOptions {
   int min_cover = 3;
   int plan_tries = 8;  // randomised greedy restarts of the pass planner; the cheapest plan wins
   int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)
+  int reg_bits = 3;    // 3: 8 amplitudes per thread, 256-thread CTAs; 4: 16 per thread, 128-thread CTAs
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
 };
 
@@ -269,34 +288,79 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
 // Build the device-facing arrays of one pass.
 inline PassHost build_pass(const std::vector<CompTerm>& comp,
                            const std::vector<std::vector<int>>& terms_of_mask,
-                           const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc) {
+                           const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc, int rb) {
   PassHost P;
   P.free_mask = pc.free_mask;
   P.L = popc64(pc.free_mask);
+  P.rb = rb;
+  const int NA = 1 << rb;
   const uint64_t S = pc.free_mask;
   // ---- roles of the free bits -------------------------------------------------------------
-  // tile bits 0..2 = the three lowest free qubits (128-byte lines / conflict-free LDS.128),
-  // tile bits 5..7 (register bits) = the free qubits least often touched by a z-mask of this
-  // pass, so that most groups have the same D for all 8 amplitudes of a thread ("flat"),
-  // the rest ascending.
+  // tile bits 0..2 = the three lowest free qubits (128-byte lines / conflict-free LDS.128);
+  // register bits (tile bits 5..5+rb-1) = the rb free qubits that minimise the shared-memory
+  // traffic of the pass: x-groups whose masks differ only in register qubits share one set of
+  // partner loads (a bundle), and a group whose z-patterns avoid the register qubits has one D
+  // for all amplitudes of a thread ("flat"); the rest ascending by how often x-masks flip them.
+  std::vector<int> fb;
+  for (int b = 0; b < n_loc; ++b)
+    if (S >> b & 1ull) fb.push_back(b);
   {
-    std::vector<int> fb;
-    for (int b = 0; b < n_loc; ++b)
-      if (S >> b & 1ull) fb.push_back(b);
     const int L = (int)fb.size();
-    std::vector<double> hits(64, 0.0);
-    for (int mi : pc.members)
-      for (int t : terms_of_mask[mi])
-        for (uint64_t m = comp[t].zl & S; m; m &= m - 1) hits[__builtin_ctzll(m)] += 1.0;
     std::vector<int> cand(fb.begin() + std::min(3, L), fb.end());
-    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return hits[a] < hits[b]; });
-    std::vector<int> reg(cand.begin(), cand.begin() + std::min<size_t>(3, cand.size()));
+    // distinct (im, z & S) per member group
+    std::vector<std::vector<uint64_t>> zsets;
+    zsets.reserve(pc.members.size());
+    for (int mi : pc.members) {
+      std::vector<uint64_t> zs;
+      for (int t : terms_of_mask[mi]) zs.push_back(((comp[t].zl & S) << 1) | (uint64_t)comp[t].im);
+      std::sort(zs.begin(), zs.end());
+      zs.erase(std::unique(zs.begin(), zs.end()), zs.end());
+      zsets.push_back(std::move(zs));
+    }
+    std::vector<int> reg;
+    const int nreg = std::min<int>(rb, (int)cand.size());
+    if ((int)cand.size() > nreg) {
+      std::vector<int> pick(nreg), best;
+      for (int i = 0; i < nreg; ++i) pick[i] = i;
+      double best_cost = -1.0;
+      std::vector<uint64_t> keys, cls;
+      while (true) {
+        uint64_t rm = 0;
+        for (int i : pick) rm |= 1ull << cand[i];
+        keys.clear();
+        double ccost = 0.0;
+        for (size_t m = 0; m < pc.members.size(); ++m) {
+          const uint64_t xl = masks[pc.members[m]];
+          keys.push_back(xl & ~rm);   // local and remote groups alike: equal outside the register qubits
+          cls.clear();
+          for (uint64_t zk : zsets[m]) cls.push_back(((zk >> 1) & rm) << 1 | (zk & 1ull));
+          std::sort(cls.begin(), cls.end());
+          ccost += (double)(std::unique(cls.begin(), cls.end()) - cls.begin()) - 1.0;
+        }
+        std::sort(keys.begin(), keys.end());
+        const double nb = (double)(std::unique(keys.begin(), keys.end()) - keys.begin());
+        // wavefronts: a bundle = NA LDS.128 of 4 wavefronts per warp; an extra class ~ NA DADD + a branch
+        const double cost = 4.0 * NA * nb + 0.5 * NA * ccost;
+        if (best_cost < 0.0 || cost < best_cost) {
+          best_cost = cost;
+          best = pick;
+        }
+        int i = nreg - 1;
+        while (i >= 0 && pick[i] == (int)cand.size() - nreg + i) --i;
+        if (i < 0) break;
+        ++pick[i];
+        for (int j = i + 1; j < nreg; ++j) pick[j] = pick[j - 1] + 1;
+      }
+      for (int i : best) reg.push_back(cand[i]);
+    } else {
+      reg = cand;
+    }
     std::sort(reg.begin(), reg.end());
     std::vector<int> rest;
     for (int b : cand)
       if (std::find(reg.begin(), reg.end(), b) == reg.end()) rest.push_back(b);
-    // the qubits most often flipped by this pass's x-masks go to the warp-uniform tile bits (8..),
-    // where the Hermitian expectation kernels can skip the partner half of a group
+    // the qubits most often flipped by this pass's x-masks go to the warp-uniform tile bits,
+    // where the Hermitian expectation kernels can skip the partner half of a bundle
     std::vector<double> xhits(64, 0.0);
     for (int mi : pc.members)
       for (uint64_t m = masks[mi] & S; m; m &= m - 1) xhits[__builtin_ctzll(m)] += 1.0;
@@ -313,13 +377,16 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     for (int j = 0; j < P.L; ++j) out |= (uint32_t)((v >> P.fbit[j]) & 1ull) << j;
     return out;
   };
+  const uint32_t reg_tmask = (uint32_t)(NA - 1) << kRegBitLo;
+  uint64_t reg_qmask = 0;
+  for (int j = kRegBitLo; j < kRegBitLo + rb && j < P.L; ++j) reg_qmask |= 1ull << P.fbit[j];
   struct Key {
     uint8_t im;
     uint32_t zt;
     int term;
   };
   struct PatTmp { int cls; uint32_t zt; std::vector<int> terms; };
-  struct SubGroup { GroupRec G; std::vector<PatTmp> pats; bool kind_a; int slot_of[2]; };
+  struct SubGroup { GroupRec G; std::vector<PatTmp> pats; int slot_of[2]; int var; bool remote; uint64_t xlo; };
   std::vector<SubGroup> subs;
   {
     uint64_t u = S;
@@ -335,7 +402,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     keys.reserve(terms_of_mask[mi].size());
     for (int t : terms_of_mask[mi])
       keys.push_back({comp[t].im, gather(comp[t].zl), t});
-    auto cls_of = [](const Key& k) { return (int)k.im * 8 + (int)((k.zt >> kRegBitLo) & 7); };
+    auto cls_of = [&](const Key& k) { return (int)k.im * NA + (int)((k.zt >> kRegBitLo) & (uint32_t)(NA - 1)); };
     std::stable_sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
       int ca = cls_of(a), cb = cls_of(b);
       if (ca != cb) return ca < cb;
@@ -351,7 +418,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       pats.push_back(std::move(pt));
       k = e;
     }
-    // sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 4095 patterns
+    // sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 2047 patterns
     // per class.  Patterns are in class order, so cut greedily.
     size_t p = 0;
     while (p < pats.size()) {
@@ -360,58 +427,70 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       std::memset(&G, 0, sizeof(G));
       G.xt = gather(xl) | (remote ? 0x80000000u : 0u);
       G.xl = xl;
+      sg.remote = remote;
+      sg.xlo = xl & ~reg_qmask;
       int count = 0, nent = 0;
       bool has_im = false;
       size_t q = p;
       while (q < pats.size() && count < kPatChunk) {
         const int cls = pats[q].cls;
-        if (nent == 0 || (G.ent[nent - 1] >> 12) != cls) {
+        if (nent == 0 || (G.ent[nent - 1] >> 11) != cls) {
           if (nent == 4) break;
-          G.ent[nent++] = (uint16_t)(cls << 12);
-        } else if ((G.ent[nent - 1] & 0xfff) == 0xfff) {
+          G.ent[nent++] = (uint16_t)(cls << 11);
+        } else if ((G.ent[nent - 1] & 0x7ff) == 0x7ff) {
           break;
         }
         G.ent[nent - 1]++;
-        if (cls >= 8) has_im = true;
+        if (cls >= NA) has_im = true;
         ++count;
         ++q;
       }
-      const bool flat = (nent == 1) && (G.ent[0] >> 12) == 0;
+      const bool flat = (nent == 1) && (G.ent[0] >> 11) == 0;
       G.meta = ((uint32_t)nent << 16) | (has_im ? (1u << 20) : 0u) | (flat ? (1u << 21) : 0u);
-      {
-        const uint32_t xt_only = G.xt & 0x7fffffffu;
-        if (!remote && xt_only != 0u) {
-          const int msb = 31 - __builtin_clz(xt_only);
-          if (msb >= 8) G.meta |= (uint32_t)(msb + 1) << 28;
-        }
-      }
-      // kind A: local, real, at most two patterns, the first (if two) of class 0.  Slot 0 of the
-      // inline copy holds the class-0 pattern (or nothing), slot 1 the other one with its class.
-      sg.kind_a = !remote && count <= 2 && (count == 1 || pats[p].cls == 0);
+      // fast variants: at most two patterns; slot 0 of the inline copy holds a real class-0 pattern
+      // (or nothing), slot 1 the other one -- real or imaginary, its class 0 or equal to the
+      // register part of the x-mask (the XX + YY pair groups, single X/Y-type terms)
+      const int xr = (int)((G.xt & reg_tmask) >> kRegBitLo);
+      const bool first_r0 = pats[p].cls == 0;
+      const bool two_slot = count == 1 || (count == 2 && first_r0);
       sg.slot_of[0] = 0;
       sg.slot_of[1] = 1;
-      if (sg.kind_a) {
-        if (count == 1 && pats[p].cls != 0) sg.slot_of[0] = 1;   // lone non-flat pattern -> slot 1
-        for (int j = 0; j < count; ++j) {
-          if (sg.slot_of[j] == 0) G.zt0 = pats[p + j].zt;
-          else {
-            G.zt1 = pats[p + j].zt;
-            G.meta |= (uint32_t)(pats[p + j].cls & 15) << 24;
+      sg.var = kVarGeneral;
+      if (two_slot) {
+        const int j1 = (count == 1 && first_r0) ? -1 : count - 1;   // pattern that goes to slot 1
+        const int c1 = j1 >= 0 ? pats[p + j1].cls : 0;
+        const int zr1 = c1 & (NA - 1);
+        if (zr1 == 0 || zr1 == xr) {
+          sg.var = (zr1 == 0 ? 0 : NA) + xr;
+          if (count == 1 && !first_r0) sg.slot_of[0] = 1;
+          for (int j = 0; j < count; ++j) {
+            if (sg.slot_of[j] == 0) G.zt0 = pats[p + j].zt;
+            else G.zt1 = pats[p + j].zt;
           }
+          if (c1 >= NA) G.meta |= 1u << 19;                         // slot 1 is imaginary
         }
-      } else {
+      }
+      if (sg.var == kVarGeneral) {
         G.zt0 = pats[p].zt;
         G.zt1 = count > 1 ? pats[p + 1].zt : 0u;
       }
+      G.meta |= (uint32_t)sg.var << 22;
       if (has_im) P.has_im = true;
       if (flat) P.n_flat++;
-      if (sg.kind_a) P.n_kind_a++;
+      if (sg.var != kVarGeneral) P.n_fast++;
       sg.pats.assign(pats.begin() + p, pats.begin() + q);
       subs.push_back(std::move(sg));
       p = q;
     }
   }
-  // chunks: consecutive sub-groups up to the staging capacity; inside a chunk kind A goes first
+  // bundle order: local before remote, then by the mask outside the register qubits, then by variant
+  std::stable_sort(subs.begin(), subs.end(), [](const SubGroup& a, const SubGroup& b) {
+    if (a.remote != b.remote) return !a.remote;
+    if (a.xlo != b.xlo) return a.xlo < b.xlo;
+    return a.var < b.var;
+  });
+  // chunks: consecutive sub-groups up to the staging capacity; a bundle cut by a chunk boundary
+  // simply becomes two bundle records
   P.pat_tptr.push_back(0);
   size_t s0 = 0;
   int g0 = 0, p0 = 0;
@@ -422,44 +501,52 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       np += (int)subs[s1].pats.size();
       ++s1;
     }
-    std::stable_sort(subs.begin() + s0, subs.begin() + s1, [](const SubGroup& a, const SubGroup& b) {
-      const int ka = a.kind_a ? (int)((a.G.meta >> 24) & 15u) : 16, kb = b.kind_a ? (int)((b.G.meta >> 24) & 15u) : 16;
-      return ka < kb;
-    });
     ChunkRec cr;
     std::memset(&cr, 0, sizeof(cr));
-    int ng_a = 0, pl = 0;
-    for (size_t si = s0; si < s1; ++si) {
-      SubGroup& sg = subs[si];
-      if (sg.kind_a) {
-        ++ng_a;
-        cr.a_cnt[(sg.G.meta >> 24) & 15u]++;
+    cr.b0 = (int32_t)P.bundles.size();
+    int pl = 0;
+    for (size_t si = s0; si < s1;) {
+      size_t se = si;
+      while (se < s1 && se - si < 255 && subs[se].remote == subs[si].remote && subs[se].xlo == subs[si].xlo) ++se;
+      BundleRec B;
+      const uint32_t xo = (subs[si].G.xt & 0x7fffffffu) & ~reg_tmask;
+      B.xo = xo | (subs[si].remote ? 0x80000000u : 0u);
+      uint32_t hbit = 0;
+      if (!subs[si].remote && xo != 0u) {
+        const int msb = 31 - __builtin_clz(xo);
+        if (msb >= kRegBitLo + rb) hbit = (uint32_t)(msb + 1);
       }
-      sg.G.meta |= (uint32_t)pl;
-      for (size_t j = 0; j < sg.pats.size(); ++j) {
-        // bit 15 of the stored pattern marks patterns of a Hermitian-paired group (doubled by the
-        // fold of the Hermitian expectation kernels, masked off by every fold)
-        P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | ((sg.G.meta >> 28) ? 0x8000u : 0u)));
-        P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
-        for (int t : sg.pats[j].terms) {
-          P.term_zb.push_back(comp[t].zl & ~S);
-          P.term_val.push_back(comp[t].val);
+      B.meta = (uint32_t)(se - si) | (hbit << 8) | ((uint32_t)(si - s0) << 16);
+      B.xlo = subs[si].xlo;
+      P.bundles.push_back(B);
+      for (; si < se; ++si) {
+        SubGroup& sg = subs[si];
+        sg.G.meta |= (uint32_t)pl | (hbit << 28);
+        for (size_t j = 0; j < sg.pats.size(); ++j) {
+          // bit 15 of the stored pattern marks patterns of a Hermitian-paired bundle (doubled by the
+          // fold of the Hermitian expectation kernels, masked off by every fold)
+          P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | (hbit ? 0x8000u : 0u)));
+          P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
+          for (int t : sg.pats[j].terms) {
+            P.term_zb.push_back(comp[t].zl & ~S);
+            P.term_val.push_back(comp[t].val);
+          }
+          P.pat_tptr.push_back((uint32_t)P.term_val.size());
+          ++pl;
         }
-        P.pat_tptr.push_back((uint32_t)P.term_val.size());
-        ++pl;
+        P.groups.push_back(sg.G);
       }
-      P.groups.push_back(sg.G);
     }
     cr.g0 = g0;
-    cr.ng = (int32_t)((s1 - s0) | ((size_t)ng_a << 16));
+    cr.ng = (int32_t)(s1 - s0);
     cr.p0 = p0;
     cr.np = np;
+    cr.nb = (int32_t)P.bundles.size() - cr.b0;
     P.chunks.push_back(cr);
     g0 += (int)(s1 - s0);
     p0 += np;
     s0 = s1;
   }
-  (void)n_loc;
   return P;
 }
 
@@ -535,7 +622,7 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
           pcs.swap(cand);
         }
       }
-      for (auto& pc : pcs) P.passes.push_back(build_pass(P.comp, tom, masks, pc, n_loc));
+      for (auto& pc : pcs) P.passes.push_back(build_pass(P.comp, tom, masks, pc, n_loc, opt.reg_bits == 4 ? 4 : 3));
     }
     out.push_back(std::move(P));
   }

@@ -3,8 +3,9 @@
 `psum_plan_export` (include/psum.h) hands out, per pass, the very arrays the kernel reads -- group
 records, pattern z-masks, inline slots, term lists, chunk records, the free/non-free bit maps.
 `run_pass` below walks them the way the kernel does (csrc/psum_kernels.cuh: tile addressing, the
-fold of out-of-tile sign bits, loop A over inline "kind A" groups with its per-class order, loop B
-over class entry lists, remote groups, Hermitian pairing), so planner output can be checked against
+fold of out-of-tile sign bits, bundles with one partner set per bundle and a register permutation
+per member, fast members with inline slots, general members with class entry lists, remote
+bundles, Hermitian pairing), so planner output can be checked against
 the oracle on the CPU.  It is a checker for the PLANNER's data, not a product path: nothing in
 qiskit_aqua_b200/ imports it.
 """
@@ -16,8 +17,11 @@ from qiskit_aqua_b200._lib import lib
 
 GROUP_DT = np.dtype([('xt', '<u4'), ('meta', '<u4'), ('zt0', '<u4'), ('zt1', '<u4'), ('cf0', '<f8'),
                      ('cf1', '<f8'), ('xl', '<u8'), ('ent', '<u2', (4,))])
-CHUNK_DT = np.dtype([('g0', '<i4'), ('ng', '<i4'), ('p0', '<i4'), ('np', '<i4'), ('a_cnt', 'u1', (16,))])
-assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 32
+BUNDLE_DT = np.dtype([('xo', '<u4'), ('meta', '<u4'), ('xlo', '<u8')])
+CHUNK_DT = np.dtype([('g0', '<i4'), ('ng', '<i4'), ('p0', '<i4'), ('np', '<i4'), ('b0', '<i4'), ('nb', '<i4'),
+                     ('pad', '<i4', (2,))])
+assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 32 and BUNDLE_DT.itemsize == 16
+VAR_GENERAL = 63
 
 
 def _ptr(a):
@@ -26,19 +30,20 @@ def _ptr(a):
 
 def export_pass(engine, g, p):
     """Arrays of pass p of global part g, or None when there is no such pass."""
-    counts = (C.c_int64 * 8)()
-    rc = lib().psum_plan_export(engine._h, g, p, counts, None, None, None, None, None, None, None, None, None)
+    counts = (C.c_int64 * 10)()
+    rc = lib().psum_plan_export(engine._h, g, p, counts, None, None, None, None, None, None, None, None, None, None)
     if rc != 0:
         return None
-    ng, npat, nterm, nch, L, nnf, has_im, hi_bit = [int(v) for v in counts]
-    out = dict(L=L, n_nonfree=nnf, has_im=bool(has_im), hi_bit=hi_bit,
-               groups=np.zeros(ng, GROUP_DT), pat_zt=np.zeros(npat, np.uint16), pat_inl=np.zeros(npat, np.uint16),
+    ng, npat, nterm, nch, L, nnf, has_im, hi_bit, nbun, rb = [int(v) for v in counts]
+    out = dict(L=L, n_nonfree=nnf, has_im=bool(has_im), hi_bit=hi_bit, rb=rb,
+               groups=np.zeros(ng, GROUP_DT), bundles=np.zeros(nbun, BUNDLE_DT),
+               pat_zt=np.zeros(npat, np.uint16), pat_inl=np.zeros(npat, np.uint16),
                pat_tptr=np.zeros(npat + 1, np.uint32), term_zb=np.zeros(nterm, np.uint64),
                term_val=np.zeros(nterm, np.float64), chunks=np.zeros(nch, CHUNK_DT),
                fbit=np.zeros(16, np.uint8), nbit=np.zeros(64, np.uint8))
     rc = lib().psum_plan_export(engine._h, g, p, counts, _ptr(out['groups']), _ptr(out['pat_zt']), _ptr(out['pat_inl']),
                                 _ptr(out['pat_tptr']), _ptr(out['term_zb']), _ptr(out['term_val']), _ptr(out['chunks']),
-                                _ptr(out['fbit']), _ptr(out['nbit']))
+                                _ptr(out['fbit']), _ptr(out['nbit']), _ptr(out['bundles']))
     assert rc == 0
     return out
 
@@ -73,36 +78,27 @@ def run_pass(ps, src, y=None, herm=False, check=True):
     """Emulates one k_pass launch over all tiles.  Adds the pass's contribution to y (if given)
     and returns sum conj(src_i) * contribution_i (with `herm`: the paired 2 Re z evaluation of the
     Hermitian expectation kernels, imaginary part forced to zero as the kernel does)."""
-    L, nnf = ps['L'], ps['n_nonfree']
+    L, nnf, rb = ps['L'], ps['n_nonfree'], ps['rb']
+    NA = 1 << rb
+    regmask = np.uint64((NA - 1) << 5)
     t = np.arange(1 << L, dtype=np.uint64)
-    t0 = t & ~np.uint64(0xE0)                      # the kernel's popc never sees the register bits
-    reg = ((t >> np.uint64(5)) & np.uint64(7)).astype(np.uint64)
+    t0 = t & ~regmask                              # the kernel's popc never sees the register bits
+    reg = (t >> np.uint64(5)) & np.uint64(NA - 1)
     off = _deposit(t, ps['fbit'][:L])
-    groups, chunks = ps['groups'], ps['chunks']
+    regq = 0                                       # register qubits as a mask over local qubits
+    for j in range(5, 5 + rb):
+        regq |= 1 << int(ps['fbit'][j])
+    groups, chunks, bundles = ps['groups'], ps['chunks'], ps['bundles']
     total = 0.0 + 0.0j
     for tile_id in range(1 << nnf):
         base = _deposit(np.array([tile_id], dtype=np.uint64), ps['nbit'][:nnf])[0]
         idx = base | off
+        idx0 = idx & ~np.uint64(regq)              # i0 | lane/warp bits, register qubits clear
         tile = src[idx]
         acc = np.zeros(1 << L, dtype=np.complex128)
 
-        def add(G, D):
-            xt = int(G['xt']) & 0x7fffffff
-            remote = int(G['xt']) >> 31
-            hbit = int(G['meta']) >> 28
-            pv = src[idx ^ np.uint64(G['xl'])] if remote else tile[t ^ np.uint64(xt)]
-            if check and not remote:
-                # tile-local xor and the full local x mask describe the same partner
-                assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
-            if check and hbit:
-                assert not remote and xt and hbit - 1 >= 8 and (xt >> (hbit - 1)) == 1
-            contrib = D * pv
-            if herm and hbit:
-                contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
-            acc[:] += contrib
-
         for ch in chunks:
-            ng, ng_a = int(ch['ng']) & 0xffff, int(ch['ng']) >> 16
+            ng = int(ch['ng'])
             p0, npat = int(ch['p0']), int(ch['np'])
             grp = groups[int(ch['g0']):int(ch['g0']) + ng].copy()
             cf = np.zeros(npat)
@@ -118,40 +114,77 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                 inl = int(ps['pat_inl'][gp])
                 if inl != 0xffff:
                     grp[inl >> 1]['cf1' if inl & 1 else 'cf0'] = v
-            g = 0
-            for cls in range(16):                                             # loop A
-                for _ in range(int(ch['a_cnt'][cls])):
-                    G = grp[g]
-                    if check:
-                        assert (int(G['meta']) >> 24) & 15 == cls and not int(G['xt']) >> 31
-                        assert ps['has_im'] or cls < 8
-                    s0 = G['cf0'] * _sign(t0 & np.uint64(G['zt0']))
-                    s1 = G['cf1'] * _sign(t0 & np.uint64(G['zt1']))
-                    flip = _sign(reg & np.uint64(cls & 7))
-                    add(G, s0 + s1 * flip if cls < 8 else s0 + 1j * s1 * flip)
-                    g += 1
-            assert g == ng_a
-            for g in range(ng_a, ng):                                         # loop B
-                G = grp[g]
-                meta = int(G['meta'])
-                p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
-                D = np.zeros(1 << L, dtype=np.complex128)
-                any_im = False
-                for e in range(nent):
-                    ent = int(G['ent'][e])
-                    cnt, cls = ent & 0xfff, ent >> 12
-                    s = np.zeros(1 << L)
-                    for j in range(cnt):
-                        if check:                       # class == register bits of the z-pattern
-                            assert (int(zt[p + j]) >> 5) & 7 == cls & 7
-                        s += cf[p + j] * _sign(t0 & zt[p + j])
-                    p += cnt
-                    any_im |= cls >= 8
-                    D += (1j if cls >= 8 else 1.0) * s * _sign(reg & np.uint64(cls & 7))
+            seen = 0
+            for B in bundles[int(ch['b0']):int(ch['b0']) + int(ch['nb'])]:
+                xo, remote = int(B['xo']) & 0x7fffffff, int(B['xo']) >> 31
+                nmem, hbit, first = int(B['meta']) & 0xff, (int(B['meta']) >> 8) & 0xff, int(B['meta']) >> 16
                 if check:
-                    assert bool(flat) == (nent == 1 and int(G['ent'][0]) >> 12 == 0)
-                    assert bool((meta >> 20) & 1) == any_im and (ps['has_im'] or not any_im)
-                add(G, D)
+                    assert first == seen and nmem >= 1 and xo & int(regmask) == 0 and int(B['xlo']) & regq == 0
+                    if hbit:
+                        assert not remote and xo and hbit - 1 >= 5 + rb and (xo >> (hbit - 1)) == 1
+                    else:
+                        assert remote or xo == 0 or xo.bit_length() - 1 < 5 + rb
+                seen += nmem
+                # the bundle's partner set: pvk[k] for a thread = tile[(t0 ^ xo) + (k << 5)]
+                for g in range(first, first + nmem):
+                    G = grp[g]
+                    meta = int(G['meta'])
+                    xt = int(G['xt']) & 0x7fffffff
+                    xr = (xt >> 5) & (NA - 1)
+                    var = (meta >> 22) & 63
+                    k = reg ^ np.uint64(xr)                                   # pv[r ^ xr]
+                    if remote:
+                        roff = _deposit(k, ps['fbit'][5:5 + rb])
+                        pv = src[(idx0 ^ np.uint64(B['xlo'])) | roff]
+                    else:
+                        pv = tile[(t0 ^ np.uint64(xo)) | (k << np.uint64(5))]
+                    if check:
+                        assert int(G['xt']) >> 31 == remote and (meta >> 28) == hbit
+                        assert int(G['xl']) & ~regq == int(B['xlo'])
+                        assert np.array_equal(pv, src[idx ^ np.uint64(G['xl'])])
+                        if not remote:
+                            assert xt & ~int(regmask) == xo
+                            assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
+                    # general evaluation from the class entry lists (every group carries them)
+                    p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
+                    D = np.zeros(1 << L, dtype=np.complex128)
+                    any_im = False
+                    for e in range(nent):
+                        ent = int(G['ent'][e])
+                        cnt, cls = ent & 0x7ff, ent >> 11
+                        sacc = np.zeros(1 << L)
+                        for j in range(cnt):
+                            if check:                   # class == register bits of the z-pattern
+                                assert (int(zt[p + j]) >> 5) & (NA - 1) == cls & (NA - 1)
+                            sacc += cf[p + j] * _sign(t0 & zt[p + j])
+                        p += cnt
+                        any_im |= cls >= NA
+                        D += (1j if cls >= NA else 1.0) * sacc * _sign(reg & np.uint64(cls & (NA - 1)))
+                    if check:
+                        assert bool(flat) == (nent == 1 and int(G['ent'][0]) >> 11 == 0)
+                        assert bool((meta >> 20) & 1) == any_im and (ps['has_im'] or not any_im)
+                    if var != VAR_GENERAL:
+                        # fast member: two inline slots, compile-time sign pattern
+                        im1 = (meta >> 19) & 1
+                        assert var < 2 * NA and bool(im1) == any_im
+                        s0 = G['cf0'] * _sign(t0 & np.uint64(G['zt0']))
+                        s1 = G['cf1'] * _sign(t0 & np.uint64(G['zt1'])) * (1j if im1 else 1.0)
+                        if var < NA:
+                            assert var == xr
+                            Df = s0 + s1
+                        else:
+                            assert var - NA == xr
+                            Df = s0 + s1 * _sign(reg & np.uint64(xr))
+                        if check:
+                            assert np.allclose(Df, D, rtol=0, atol=1e-13 * (1.0 + np.abs(D).max()))
+                        D = Df.astype(np.complex128)
+                    elif check:
+                        assert not (meta >> 19) & 1
+                    contrib = D * pv
+                    if herm and hbit:
+                        contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
+                    acc += contrib
+            assert seen == ng
         if y is not None:
             y[idx] += acc
         total += np.vdot(tile, acc)

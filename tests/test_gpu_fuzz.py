@@ -37,7 +37,7 @@ def _random_operator(rng, n):
     return x, z, ypow, c.astype(np.complex128)
 
 
-@pytest.mark.parametrize('seed', range(40))
+@pytest.mark.parametrize('seed', range(64))
 def test_fuzz_apply_and_expect(seed):
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(1, 15))
@@ -46,7 +46,7 @@ def test_fuzz_apply_and_expect(seed):
     if n >= 11:
         opts = {'tile_bits': int(rng.integers(11, min(13, n) + 1)), 'low_bits': int(rng.integers(1, 7)),
                 'min_cover': int(rng.integers(1, 5)), 'late_bits': int(rng.integers(0, 3)),
-                'herm_pairing': int(rng.integers(0, 2))}
+                'herm_pairing': int(rng.integers(0, 2)), 'reg_bits': int(rng.integers(3, 5))}
         if rng.random() < 0.15:
             opts['kernel'] = 1
     psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
@@ -87,7 +87,7 @@ def test_sharded_parts_emulated_on_one_gpu(world, n, seed):
     e_with_y = 0.0
     e_contrib = 0.0
     for r in range(world):
-        eng = PauliSumEngine(n, x, z, ypow, c)
+        eng = PauliSumEngine(n, x, z, ypow, c, {'reg_bits': 3 + (seed + r) % 2})
         eng.shard(r, world)
         y = torch.zeros(N_loc, dtype=torch.complex128, device='cuda')
         parts = [g for g in range(world) if len(eng.shard_terms(g)[0])]

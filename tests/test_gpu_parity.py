@@ -42,12 +42,29 @@ def test_random_complex_operator(n):
     _check(n, x, z, y, c, seed=n)
 
 
+@pytest.mark.parametrize('reg_bits', [3, 4])
 @pytest.mark.parametrize('tile_bits,low_bits', [(11, 4), (12, 4), (13, 4), (12, 1), (12, 6), (13, 3)])
-def test_two_local_tiled(tile_bits, low_bits):
+def test_two_local_tiled(tile_bits, low_bits, reg_bits):
     n, x, z, y, c = W.two_local_random(16, 500, seed=16)
-    eng = _check(n, x, z, y, c, {'tile_bits': tile_bits, 'low_bits': low_bits})
+    eng = _check(n, x, z, y, c, {'tile_bits': tile_bits, 'low_bits': low_bits, 'reg_bits': reg_bits})
     info = eng.info()
     assert info['n_passes'] >= 1 and info['tile_bits'] == tile_bits
+    assert info['n_bundles'] < info['n_group_records']        # partner loads are shared
+
+
+@pytest.mark.parametrize('reg_bits', [3, 4])
+@pytest.mark.parametrize('kind', ['c4', 'c5', 'molecular'])
+def test_benchmark_families_both_register_widths(kind, reg_bits):
+    if kind == 'c4':
+        n, x, z, y, c = W.ising_heisenberg(18, n_triples=3000, seed=30)
+    elif kind == 'c5':
+        n, x, z, y, c = W.random_weighted_paulis(18, 3000, 4, seed=34)
+    else:
+        n, x, z, y, c = W.molecular_style(14)
+    eng = _check(n, x, z, y, c, {'reg_bits': reg_bits})
+    psi = _state(n, 5)
+    ref = np.vdot(psi, co.apply(n, x, z, y, c, psi))
+    assert abs(eng.expect_host(psi) - ref) <= RTOL * max(1.0, abs(ref))
 
 
 def test_streaming_kernel_forced():

@@ -1,7 +1,8 @@
 """CPU verification of the pass planner: the arrays `k_pass` reads (exported with
 psum_plan_export) are executed by the numpy interpreter in tests/plan_interpreter.py and compared
-with the oracle -- tile addressing, fold lists, class entries, inline kind-A slots, chunking,
-sub-groups, remote groups, Hermitian pairing flags, late-bit plans and sharded parts."""
+with the oracle -- tile addressing, fold lists, bundles (one partner set, a register permutation per
+member), class entries, inline fast slots, chunking, sub-groups, remote bundles, Hermitian pairing
+flags, late-bit plans and sharded parts; for 8 and 16 amplitudes per thread (reg_bits 3 and 4)."""
 import numpy as np
 import pytest
 
@@ -54,6 +55,13 @@ CASES = [
     (13, 600, {'tile_bits': 11, 'late_bits': 2}, {}),                    # host-state plan (early passes chunk-local)
     (13, 300, {'tile_bits': 13}, {}),
     (12, 600, {'tile_bits': 11}, {'no_y': True, 'complex_weights': False}),   # real-only passes (IM = false kernels)
+    (11, 300, {'tile_bits': 11, 'reg_bits': 4}, {}),
+    (13, 500, {'tile_bits': 12, 'reg_bits': 4}, {'max_weight': 5}),
+    (12, 3000, {'tile_bits': 12, 'reg_bits': 4}, {}),
+    (12, 1500, {'tile_bits': 11, 'reg_bits': 4}, {'x_pool': 6}),
+    (14, 200, {'tile_bits': 11, 'reg_bits': 4}, {'dense': 12}),
+    (13, 300, {'tile_bits': 13, 'reg_bits': 4}, {}),
+    (12, 600, {'tile_bits': 11, 'reg_bits': 4}, {'no_y': True, 'complex_weights': False}),
 ]
 
 
@@ -66,6 +74,8 @@ def test_exported_plan_reproduces_oracle(n, T, opts, kw):
     passes = pi.export_part(eng, 0)
     assert len(passes) == info['n_passes'] > 0
     assert sum(len(ps['groups']) for ps in passes) == info['n_group_records']
+    assert sum(len(ps['bundles']) for ps in passes) == info['n_bundles'] <= info['n_group_records']
+    assert all(ps['rb'] == opts.get('reg_bits', 3) for ps in passes)
     assert sum(len(ps['pat_zt']) for ps in passes) == info['n_patterns']
     assert sum(len(ps['term_val']) for ps in passes) == info['n_component_terms']     # every term exactly once
     if kw.get('dense'):
@@ -89,7 +99,8 @@ def test_exported_plan_reproduces_oracle(n, T, opts, kw):
     assert abs(e - np.vdot(psi, want)) <= 1e-12 * scale
 
 
-@pytest.mark.parametrize('n,T,opts', [(11, 400, {'tile_bits': 11}), (13, 700, {'tile_bits': 11}), (12, 2500, {'tile_bits': 12})])
+@pytest.mark.parametrize('n,T,opts', [(11, 400, {'tile_bits': 11}), (13, 700, {'tile_bits': 11}), (12, 2500, {'tile_bits': 12}),
+                                      (13, 700, {'tile_bits': 12, 'reg_bits': 4})])
 def test_hermitian_pairing_flags(n, T, opts):
     """Expectation with the pairing the HERM kernels use: groups flagged with a warp-uniform top
     x bit are evaluated on half of the amplitudes with doubled patterns; equals Re <psi|H|psi>."""
@@ -102,9 +113,9 @@ def test_hermitian_pairing_flags(n, T, opts):
     assert flagged > 0
     for ps in passes:       # bit 15 of a stored pattern <=> its group is paired
         for ch in ps['chunks']:
-            for G in ps['groups'][int(ch['g0']):int(ch['g0']) + (int(ch['ng']) & 0xffff)]:
+            for G in ps['groups'][int(ch['g0']):int(ch['g0']) + int(ch['ng'])]:
                 first = int(ch['p0']) + (int(G['meta']) & 0xffff)
-                count = sum(int(e) & 0xfff for e in G['ent'][:(int(G['meta']) >> 16) & 7])
+                count = sum(int(e) & 0x7ff for e in G['ent'][:(int(G['meta']) >> 16) & 7])
                 marked = ps['pat_zt'][first:first + count] >> 15
                 assert np.all(marked == (1 if int(G['meta']) >> 28 else 0))
     psi = random_state(n, rng)
@@ -113,8 +124,9 @@ def test_hermitian_pairing_flags(n, T, opts):
     assert got.imag == 0.0 and abs(got.real - want.real) <= 1e-12 * max(1.0, abs(want))
 
 
+@pytest.mark.parametrize('rb', [3, 4])
 @pytest.mark.parametrize('world', [2, 4])
-def test_sharded_parts_reproduce_oracle(world):
+def test_sharded_parts_reproduce_oracle(world, rb):
     """Every rank's parts (global x-part g: partner shard r ^ g, rank sign folded into the weights)
     executed by the interpreter give that rank's slice of H.psi."""
     n, T = 13, 500
@@ -126,7 +138,7 @@ def test_sharded_parts_reproduce_oracle(world):
     shards = psi.reshape(world, 1 << n_loc)
     seen_parts = set()
     for rank in range(world):
-        eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11})
+        eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11, 'reg_bits': rb})
         eng.shard(rank, world)
         y = np.zeros(1 << n_loc, dtype=np.complex128)
         for g in range(world):
@@ -138,8 +150,9 @@ def test_sharded_parts_reproduce_oracle(world):
     assert len(seen_parts) > 1
 
 
+@pytest.mark.parametrize('rb', [3, 4])
 @pytest.mark.parametrize('kind', ['c4_style', 'molecular', 'c5_style'])
-def test_bench_workload_shapes(kind):
+def test_bench_workload_shapes(kind, rb):
     """The benchmark operator families at 13-14 qubits: TFIM + Heisenberg + 3-local part (C4),
     Jordan-Wigner molecular-style sum (C3), random weight <= 4 Paulis (C5)."""
     from qiskit_aqua_b200 import workloads as W
@@ -152,7 +165,9 @@ def test_bench_workload_shapes(kind):
     else:
         n = 14
         _, x, z, ypow, c = W.random_weighted_paulis(n, 2000, 4, seed=34)
-    eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11})
+    eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11, 'reg_bits': rb})
+    info = eng.info()
+    assert info['n_bundles'] < info['n_group_records']            # partner sets are shared
     passes = pi.export_part(eng, 0)
     rng = np.random.default_rng(3)
     psi = random_state(n, rng)
