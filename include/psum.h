@@ -81,6 +81,12 @@ int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[10], void* gr
                      uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
                      double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles);
 
+/* Lower bounds of one H.psi on this rank computed from the plan (host only): out[0] = DRAM bytes
+ * (store != 0: y is written), out[1] = shared-memory wavefronts, out[2] = group records, out[3] =
+ * partner load sets.  bench.py divides them by the measured HBM bandwidth and by the shared-memory
+ * pipe rate (1 wavefront per clock per SM) to get the roofline floors. */
+int psum_plan_floors(psum_handle_t h, int store, double out[4]);
+
 /* ---- H.psi and <psi|H|psi> ------------------------------------------------------------ */
 /* y = H psi ; if expect_out != NULL also expect_out = {Re,Im} of sum_i conj(psi_i) y_i (host
  * pointer, forces a stream sync).  Replaces `mat_op._matrix.dot(psi)` (+ np.vdot) at
@@ -180,6 +186,12 @@ int psum_apply_sharded(psum_handle_t h, const void* psi_dev, void* y_dev, void* 
  * H2D copy chunk by chunk and the NCCL exchanges start when the last chunk has landed. */
 int psum_expect_sharded_host(psum_handle_t h, const void* psi_host, void* psi_dev, void* recv_dev,
                              uint64_t recv_amps, double out[2], psum_stream_t stream);
+/* Instrumentation of the last psum_apply_sharded / psum_expect_sharded_host call made with option
+ * "profile_exchange" = 1: out[0] = exchanges, out[1] = bytes sent (= received) per exchange, out[2] =
+ * sum of the exchange intervals on the communication stream in ms (CUDA events), out[3] = span from
+ * the first post to the last arrival in ms.  Option "skip_exchange" = 1 issues the same launches
+ * without the NCCL calls (compute-only timing; results are meaningless). */
+int psum_exchange_stats(psum_handle_t h, double out[4]);
 /* Host-side eigen-solver test hook (no device): which = 0 dense Jacobi (A = n*n), 1 tridiagonal
  * QL (A = d[n], e[n]).  w[n] ascending, V n*n eigenvectors in columns (may be NULL). */
 int psum_test_eigh(int which, int n, const double* A, double* w, double* V);

@@ -432,7 +432,7 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
       v[8] += (int64_t)ps.pat_zt.size();
       v[12] += ps.n_flat;
       v[14] += ps.n_fast;
-      v[15] += (int64_t)ps.bundles.size();
+      v[15] += (int64_t)ps.bundles.size() + ps.n_singles;
       v[13] += (int64_t)ps.groups.size();
       v[10] = ps.L;
     }
@@ -464,6 +464,45 @@ extern "C" int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask
   if (n_groups) *n_groups = ps.n_xgroups;
   if (n_remote_groups) *n_remote_groups = ps.n_remote;
   if (n_patterns) *n_patterns = (int64_t)ps.pat_zt.size();
+  return PSUM_OK;
+}
+
+// Lower bounds of one H.psi on this rank, from the plan the kernels execute:
+//   out[0] DRAM bytes: a pass reads its source tile once, reads the old y (every pass but the first of
+//          the step; none without `store`) and writes y; a remote bundle re-reads one partner vector
+//   out[1] shared-memory wavefronts: per warp and round a partner load set (bundle or single) costs
+//          2^RB LDS.128 of 4 wavefronts, a fast member 2 record reads, a general member 3 + one per
+//          pattern, a bundle header 1; staging the tile writes 16 B per amplitude
+//   out[2] group records, out[3] partner load sets
+extern "C" int psum_plan_floors(psum_handle_t h, int store, double out[4]) {
+  if (!h || !out) return fail(PSUM_ERR_INVALID, "null argument");
+  if (!h->planned) PS_TRY(plan(h));
+  const double N = ldexp(1.0, h->n_loc);
+  double dram = 0.0, wf = 0.0, ngr = 0.0, nsets = 0.0;
+  bool first = true;
+  for (const PartHost& P : h->parts) {
+    if (P.passes.empty()) {   // streaming kernel: one partner read per x-group
+      dram += 16.0 * N * ((double)P.sgroups.size() + (store ? (first ? 1.0 : 2.0) : 0.0));
+      first = false;
+      continue;
+    }
+    for (const PassHost& ps : P.passes) {
+      const double na = (double)(1 << ps.rb);
+      const double warp_rounds = N / (32.0 * na);
+      const double local_sets = (double)ps.n_singles + (double)ps.bundles.size() - (double)ps.n_remote_bundles;
+      dram += 16.0 * N * (1.0 + (store ? (first ? 1.0 : 2.0) : 0.0) + (double)ps.n_remote_bundles);
+      wf += warp_rounds * (4.0 * na * local_sets + 2.0 * (double)ps.n_fast + 3.0 * (double)ps.n_general +
+                           (double)ps.n_general_patterns + (double)ps.bundles.size());
+      wf += N * 16.0 / 128.0;
+      ngr += (double)ps.groups.size();
+      nsets += (double)ps.n_singles + (double)ps.bundles.size();
+      first = false;
+    }
+  }
+  out[0] = dram;
+  out[1] = wf;
+  out[2] = ngr;
+  out[3] = nsets;
   return PSUM_OK;
 }
 

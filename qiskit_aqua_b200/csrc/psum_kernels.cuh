@@ -108,33 +108,31 @@ __device__ __forceinline__ void add_class(double (&D)[ND], double s) {
   }
 }
 
-// fast variants: yacc[r] += d_r * pv[r ^ XR] with d_r = dp, or dm where popc(r & XR) is odd (V >= NA)
-template <int NA, int V>
+// fast members: yacc[r] += d_r * pv[PRE ? r : r ^ XR], d_r = dp, or dm where popc(r & XR) is odd
+// (PRE: the loads already applied the register permutation)
+template <int NA, int XR, bool PRE>
 __device__ __forceinline__ void fast_fma(double2 (&yacc)[NA], const double2 (&pv)[NA], double dp, double dm) {
-  if constexpr (V < 2 * NA) {
-    constexpr int XR = V & (NA - 1);
-    constexpr bool SGN = V >= NA;
+  if constexpr (XR < NA) {
 #pragma unroll
     for (int r = 0; r < NA; ++r) {
-      const double d = (SGN && (__popc(r & XR) & 1)) ? dm : dp;
-      yacc[r].x = fma(d, pv[r ^ XR].x, yacc[r].x);
-      yacc[r].y = fma(d, pv[r ^ XR].y, yacc[r].y);
+      const double d = (__popc(r & XR) & 1) ? dm : dp;
+      const double2 v = pv[PRE ? r : (r ^ XR)];
+      yacc[r].x = fma(d, v.x, yacc[r].x);
+      yacc[r].y = fma(d, v.y, yacc[r].y);
     }
   }
 }
-
-// the same with an imaginary slot 1: yacc[r] += (s0 + i d_r) * pv[r ^ XR], d_r = +-s1
-template <int NA, int V>
-__device__ __forceinline__ void fast_fma_im(double2 (&yacc)[NA], const double2 (&pv)[NA], double s0, double s1) {
-  if constexpr (V < 2 * NA) {
-    constexpr int XR = V & (NA - 1);
-    constexpr bool SGN = V >= NA;
-    const double n1 = -s1;
+// the same with an imaginary slot 1: yacc[r] += (s0 + i d_r) * pv[..], d_r = da / db
+template <int NA, int XR, bool PRE>
+__device__ __forceinline__ void fast_fma_im(double2 (&yacc)[NA], const double2 (&pv)[NA], double s0, double da,
+                                            double db) {
+  if constexpr (XR < NA) {
 #pragma unroll
     for (int r = 0; r < NA; ++r) {
-      const bool neg = SGN && (__popc(r & XR) & 1);
-      yacc[r].x = fma(s0, pv[r ^ XR].x, fma(neg ? s1 : n1, pv[r ^ XR].y, yacc[r].x));
-      yacc[r].y = fma(s0, pv[r ^ XR].y, fma(neg ? n1 : s1, pv[r ^ XR].x, yacc[r].y));
+      const double d = (__popc(r & XR) & 1) ? db : da;
+      const double2 v = pv[PRE ? r : (r ^ XR)];
+      yacc[r].x = fma(s0, v.x, fma(-d, v.y, yacc[r].x));
+      yacc[r].y = fma(s0, v.y, fma(d, v.x, yacc[r].y));
     }
   }
 }
@@ -235,6 +233,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
     for (int b = tid; b < ch.nb; b += NT)
       bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch.b0)[b];
+    if (tid < 3) grp4[ch.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
+    if (tid == 3) bun4[ch.nb] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (int p = tid; p < ch.np; p += NT) {
       const int gp = ch.p0 + p;
@@ -291,90 +291,143 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           stage_chunk(ch, base);
           __syncthreads();
         }
-        for (int b = 0; b < ch.nb; ++b) {
-          const uint4 B = bun4[b];
-          if (HERM) {  // partner half of a paired bundle (warp-uniform)
-            const uint32_t hb = (B.y >> 8) & 0xffu;
-            if (hb && ((t0 >> (hb - 1u)) & 1u)) continue;
-          }
-          // one set of partner amplitudes for every member of the bundle
-          double2 pv[NA];
-          if (!(B.x >> 31)) {
-            const double2* pp = tile + (t0 ^ B.x);   // register bits clear on both sides
+        // ---- singles: a fast group alone in its bundle; one straight-line loop per (im, xr) with
+        // the register permutation folded into the load offsets -----------------------------------
+        {
+          int g = 0;
 #pragma unroll
-            for (int r = 0; r < NA; ++r) pv[r] = pp[r << 5];
-          } else {
-            const char* pp = reinterpret_cast<const char*>(src + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
+          for (int s = 0; s < ND; ++s) {
+            constexpr int kUnroll = RB == 3 ? 2 : 1;
+            const int gend = g + (int)ch.s_cnt[s];
+            const int XR = s & (NA - 1);   // compile-time after unrolling
+#pragma unroll(kUnroll)
+            for (; g < gend; ++g) {
+              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+              if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
+              const double2* pp = tile + ((t0 ^ h0.x) & ~((uint32_t)(NA - 1) << 5));
+              double2 pv[NA];
 #pragma unroll
-            for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
-          }
-          int g = (int)(B.y >> 16);
-          const int gend = g + (int)(B.y & 0xffu);
-          for (; g < gend; ++g) {
-            const uint4 h0 = grp4[3 * g];
-            const uint32_t var = (h0.y >> 22) & 63u;
-            if (var < 2u * NA) {
-              // fast member: <= 2 patterns, coefficients inline in the record
-              const uint4 hc = grp4[3 * g + 1];
+              for (int r = 0; r < NA; ++r) pv[r] = pp[(r ^ XR) << 5];
+              const uint32_t q1 = (uint32_t)__popc(h0.w & t0);
+              const uint32_t sg = (h0.y >> (22 + RB)) & 1u;   // slot-1 class = xr: odd r flip its sign
               const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
-              const double s1 = __hiloint2double((int)(hc.w ^ ((uint32_t)__popc(h0.w & t0) << 31)), (int)hc.z);
-              if (IM && ((h0.y >> 19) & 1u)) {
-                switch (var) {
-#define PSUM_FAST_CASE(V) case V: fast_fma_im<NA, V>(yacc, pv, s0, s1); break;
-                  PSUM_REP32(PSUM_FAST_CASE)
-#undef PSUM_FAST_CASE
-                }
-                continue;
+              const double s1a = __hiloint2double((int)(hc.w ^ (q1 << 31)), (int)hc.z);
+              const double s1b = __hiloint2double((int)(hc.w ^ ((q1 + sg) << 31)), (int)hc.z);
+              if (s < NA) {
+#define PSUM_SINGLE_CASE(V) if (XR == V) fast_fma<NA, V, true>(yacc, pv, s0 + s1a, s0 + s1b);
+                PSUM_REP32(PSUM_SINGLE_CASE)
+#undef PSUM_SINGLE_CASE
+              } else {
+#define PSUM_SINGLE_CASE(V) if (XR == V) fast_fma_im<NA, V, true>(yacc, pv, s0, s1a, s1b);
+                PSUM_REP32(PSUM_SINGLE_CASE)
+#undef PSUM_SINGLE_CASE
               }
-              const double dp = s0 + s1, dm = s0 - s1;
-              switch (var) {
-#define PSUM_FAST_CASE(V) case V: fast_fma<NA, V>(yacc, pv, dp, dm); break;
-                PSUM_REP32(PSUM_FAST_CASE)
-#undef PSUM_FAST_CASE
-              }
+            }
+          }
+        }
+        // ---- bundles: one set of partner amplitudes, a register permutation per member ----------
+        // The member records are consecutive over all bundles of the chunk: the next record (and
+        // the next bundle header) is fetched while the current member is being applied.
+        {
+          int g = (int)ch.ns;
+          uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+          uint4 B = bun4[0];
+          for (int b = 0; b < ch.nb; ++b) {
+            const uint4 Bn = bun4[b + 1];
+            const int gend = g + (int)(B.y & 0xffu);
+            bool skip = false;
+            if (HERM) {  // partner half of a paired bundle (warp-uniform)
+              const uint32_t hb = (B.y >> 8) & 0xffu;
+              skip = hb && ((t0 >> (hb - 1u)) & 1u);
+            }
+            if (skip) {
+              g = gend;
+              h0 = grp4[3 * g];
+              hc = grp4[3 * g + 1];
+              B = Bn;
               continue;
             }
-            // general member: class entry lists
-            const uint4 h2 = grp4[3 * g + 2];
-            const uint32_t xr = (h0.x >> 5) & (uint32_t)(NA - 1);
-            int p = (int)(h0.y & 0xffffu);
-            if ((h0.y >> 21) & 1u) {
-              // flat: one real class-0 entry -> the same D for all amplitudes of the thread
-              const double s = pattern_sum(pat4, p, (int)(h2.z & 0x7ffu), t0);
-              switch (xr) {
-#define PSUM_FLAT_CASE(V) case V: fast_fma<NA, (V < NA ? V : 0)>(yacc, pv, s, s); break;
-                PSUM_REP32(PSUM_FLAT_CASE)
-#undef PSUM_FLAT_CASE
-              }
-              continue;
-            }
-            const int nent = (int)((h0.y >> 16) & 7u);
-            uint64_t ents = (uint64_t)h2.z | ((uint64_t)h2.w << 32);
-            double D[ND];
+            double2 pv[NA];
+            if (!(B.x >> 31)) {
+              const double2* pp = tile + (t0 ^ B.x);   // register bits clear on both sides
 #pragma unroll
-            for (int r = 0; r < ND; ++r) D[r] = 0.0;
-            for (int e = 0; e < nent; ++e) {
-              const uint32_t ent = (uint32_t)ents & 0xffffu;
-              ents >>= 16;
-              const double s = pattern_sum(pat4, p, (int)(ent & 0x7ffu), t0);
-              switch (ent >> 11) {
-#define PSUM_CLASS_CASE(C) case C: add_class<NA, C, ND>(D, s); break;
-                PSUM_REP32(PSUM_CLASS_CASE)
-#undef PSUM_CLASS_CASE
-              }
-            }
-            if (IM && ((h0.y >> 20) & 1u)) {
-              switch (xr) {
-#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, IM, ND>(yacc, pv, D); break;
-                PSUM_REP32(PSUM_PERM_CASE)
-#undef PSUM_PERM_CASE
-              }
+              for (int r = 0; r < NA; ++r) pv[r] = pp[r << 5];
             } else {
-              switch (xr) {
-#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, false, ND>(yacc, pv, D); break;
-                PSUM_REP32(PSUM_PERM_CASE)
+              const char* pp = reinterpret_cast<const char*>(src + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
+#pragma unroll
+              for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
+            }
+            B = Bn;
+            for (; g < gend; ++g) {
+              const uint4 n0 = grp4[3 * g + 3], nc = grp4[3 * g + 4];   // next member (or the overrun slot)
+              const uint32_t var = (h0.y >> 22) & 63u;
+              const uint32_t xr = (h0.x >> 5) & (uint32_t)(NA - 1);
+              if (var < 2u * NA) {
+                // fast member: <= 2 patterns, coefficients inline in the record
+                const uint32_t q1 = (uint32_t)__popc(h0.w & t0);
+                const uint32_t sg = var >> RB;
+                const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
+                const double s1a = __hiloint2double((int)(hc.w ^ (q1 << 31)), (int)hc.z);
+                const double s1b = __hiloint2double((int)(hc.w ^ ((q1 + sg) << 31)), (int)hc.z);
+                if (IM && ((h0.y >> 19) & 1u)) {
+                  switch (xr) {
+#define PSUM_FAST_CASE(V) case V: fast_fma_im<NA, V, false>(yacc, pv, s0, s1a, s1b); break;
+                    PSUM_REP32(PSUM_FAST_CASE)
+#undef PSUM_FAST_CASE
+                  }
+                } else {
+                  const double dp = s0 + s1a, dm = s0 + s1b;
+                  switch (xr) {
+#define PSUM_FAST_CASE(V) case V: fast_fma<NA, V, false>(yacc, pv, dp, dm); break;
+                    PSUM_REP32(PSUM_FAST_CASE)
+#undef PSUM_FAST_CASE
+                  }
+                }
+              } else {
+                // general member: class entry lists
+                const uint4 h2 = grp4[3 * g + 2];
+                int p = (int)(h0.y & 0xffffu);
+                if ((h0.y >> 21) & 1u) {
+                  // flat: one real class-0 entry -> the same D for all amplitudes of the thread
+                  const double sf = pattern_sum(pat4, p, (int)(h2.z & 0x7ffu), t0);
+                  switch (xr) {
+#define PSUM_FLAT_CASE(V) case V: fast_fma<NA, V, false>(yacc, pv, sf, sf); break;
+                    PSUM_REP32(PSUM_FLAT_CASE)
+#undef PSUM_FLAT_CASE
+                  }
+                } else {
+                  const int nent = (int)((h0.y >> 16) & 7u);
+                  uint64_t ents = (uint64_t)h2.z | ((uint64_t)h2.w << 32);
+                  double D[ND];
+#pragma unroll
+                  for (int r = 0; r < ND; ++r) D[r] = 0.0;
+                  for (int e = 0; e < nent; ++e) {
+                    const uint32_t ent = (uint32_t)ents & 0xffffu;
+                    ents >>= 16;
+                    const double sc = pattern_sum(pat4, p, (int)(ent & 0x7ffu), t0);
+                    switch (ent >> 11) {
+#define PSUM_CLASS_CASE(C) case C: add_class<NA, C, ND>(D, sc); break;
+                      PSUM_REP32(PSUM_CLASS_CASE)
+#undef PSUM_CLASS_CASE
+                    }
+                  }
+                  if (IM && ((h0.y >> 20) & 1u)) {
+                    switch (xr) {
+#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, IM, ND>(yacc, pv, D); break;
+                      PSUM_REP32(PSUM_PERM_CASE)
 #undef PSUM_PERM_CASE
+                    }
+                  } else {
+                    switch (xr) {
+#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, false, ND>(yacc, pv, D); break;
+                      PSUM_REP32(PSUM_PERM_CASE)
+#undef PSUM_PERM_CASE
+                    }
+                  }
+                }
               }
+              h0 = n0;
+              hc = nc;
             }
           }
         }

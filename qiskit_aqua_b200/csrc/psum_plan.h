@@ -69,6 +69,9 @@ struct GroupRec {     // 48 bytes
   double cf0, cf1;    // their folded coefficients: written in SHARED memory by the fold
   uint64_t xl;        // full local x mask (partner index = i ^ xl)
   uint16_t ent[4];    // non-empty classes: (cls << 11) | count ; cls = im*NA + ((zt >> 5) & (NA-1))
+  // variant 62 (quadratic group): bytes 8..31 (zt0 .. cf1) hold instead u8 seg[17] (pattern offsets of
+  // the segments, seg[nseg] = pattern count), then at byte 30 a u16 offset (in doubles) of the
+  // group's tables inside the chunk's quad arena; ent[] is unused
 };
 static_assert(sizeof(GroupRec) == 48, "GroupRec layout");
 
@@ -78,20 +81,46 @@ struct PatRec {       // 16 bytes, staged in shared memory per chunk (cf is writ
   uint32_t pad;
 };
 
-struct ChunkRec {  // 32 bytes
+struct ChunkRec {  // 64 bytes
   int32_t g0;  // first group
   int32_t ng;  // groups in the chunk
   int32_t p0, np;
-  int32_t b0, nb;  // bundles of the chunk (members are consecutive groups, in bundle order)
-  int32_t pad[2];
+  int32_t b0, nb;  // bundles of the chunk: they cover the groups [ns, ng) in bundle order
+  uint16_t ns;     // the first ns groups are "singles": local fast groups that are alone in their
+                   // bundle.  They need no bundle record and are sorted by s = im*NA + xr so that each
+                   // (im, xr) runs its own straight-line loop with a compile-time register permutation
+  uint16_t nq;     // quadratic groups in the chunk (their tables are rebuilt per tile)
+  uint32_t pad1;
+  uint8_t s_cnt[32];  // singles per s
 };
-static_assert(sizeof(ChunkRec) == 32, "ChunkRec layout");
+static_assert(sizeof(ChunkRec) == 64, "ChunkRec layout");
 
 constexpr int kMaxTileBits = 13;
 constexpr int kRegBitLo = 5;     // tile bits 5 .. 5+RB-1 live in registers (2^RB amplitudes per thread)
 constexpr int kVarGeneral = 63;
+constexpr int kVarQuad = 62;
+// "Quadratic" groups: every in-tile z-pattern is real and touches at most two tile bits (ZZ couplings,
+// Z X Z decorations, ...).  D(lane, w, r) of such a group is a quadratic form in the signs of the tile
+// bits; it separates into small tables over the lane bits and over the warp/round bits that are
+// rebuilt per tile, so a thread evaluates ~14 table reads instead of one record per pattern:
+//   class {}      A0  = T_L[lane] + T_W[w] + sum_j s_j(w) C_j[lane]        (j over the warp/round bits)
+//   class {i}     A_i = TL_i[lane] + TW_i[w]                               (i over the register bits)
+//   class {i,i'}  K[mask]
+// Table layout of one group (doubles): (1 + nW + RB) lane tables of 32, (1 + RB) w tables of 2^nW,
+// K[2^RB].  The group's patterns are sorted into segments, one per table (seg offsets in the record):
+//   0: lane-only (incl. the constant)  1: w-only  2+j: {lane bit, w bit j}  2+nW+i: {reg i} (+ lane bit)
+//   2+nW+RB+i: {w bit, reg i}  2+nW+2RB: {reg i, reg i'}
+constexpr int kQuadMinPatterns = 6;
+#ifndef PSUM_QUAD_DOUBLES
+#define PSUM_QUAD_DOUBLES 2048
+#endif
+constexpr int kQuadDoubles = PSUM_QUAD_DOUBLES;   // shared-memory arena of the quad tables of a chunk
+inline int quad_table_doubles(int L, int rb) {
+  const int nW = L - kRegBitLo - rb;
+  return (1 + nW + rb) * 32 + (1 + rb) * (1 << nW) + (1 << rb);
+}
 #ifndef PSUM_PAT_CHUNK
-#define PSUM_PAT_CHUNK 1024
+#define PSUM_PAT_CHUNK 768
 #endif
 #ifndef PSUM_GRP_CHUNK
 #define PSUM_GRP_CHUNK 128
@@ -109,6 +138,9 @@ struct PassHost {
   int64_t n_flat = 0;          // groups whose D is the same for all register amplitudes
   int64_t n_fast = 0;          // groups served by a fast variant (real, <= 2 inline patterns)
   std::vector<BundleRec> bundles;
+  int64_t n_singles = 0;       // fast groups alone in their bundle (no bundle record)
+  int64_t n_remote_bundles = 0, n_general = 0, n_general_patterns = 0;   // for the cost model
+  int64_t n_quad = 0;          // quadratic groups (table evaluation)
   std::vector<GroupRec> groups;
   std::vector<uint16_t> pat_zt;
   std::vector<uint16_t> pat_inl;   // (group index in chunk) * 2 + slot for inlined patterns, else 0xffff
@@ -418,6 +450,50 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       pats.push_back(std::move(pt));
       k = e;
     }
+    // quadratic group?  (all patterns real, at most two tile bits each)
+    {
+      bool quad = (int)pats.size() >= kQuadMinPatterns && pats.size() <= 255 && quad_table_doubles(P.L, rb) <= kQuadDoubles;
+      for (const PatTmp& pt : pats)
+        if (pt.cls >= NA || __builtin_popcount(pt.zt) > 2) quad = false;
+      if (quad) {
+        const int nW = P.L - kRegBitLo - rb;
+        auto seg_of = [&](uint32_t zt) {
+          const uint32_t zl = zt & 31u, zr = (zt >> kRegBitLo) & (uint32_t)(NA - 1), zw = zt >> (kRegBitLo + rb);
+          const int nl = __builtin_popcount(zl), nr = __builtin_popcount(zr), nw = __builtin_popcount(zw);
+          if (nr == 0) {
+            if (nw == 0) return 0;
+            if (nl == 0) return 1;
+            return 2 + __builtin_ctz(zw);
+          }
+          if (nr == 1) return (nw == 0 ? 2 + nW : 2 + nW + rb) + __builtin_ctz(zr);
+          return 2 + nW + 2 * rb;
+          (void)nl;
+        };
+        std::stable_sort(pats.begin(), pats.end(), [&](const PatTmp& a, const PatTmp& b) { return seg_of(a.zt) < seg_of(b.zt); });
+        SubGroup sg;
+        GroupRec& G = sg.G;
+        std::memset(&G, 0, sizeof(G));
+        G.xt = gather(xl) | (remote ? 0x80000000u : 0u);
+        G.xl = xl;
+        sg.remote = remote;
+        sg.xlo = xl & ~reg_qmask;
+        sg.var = kVarQuad;
+        sg.slot_of[0] = 0;
+        sg.slot_of[1] = 1;
+        G.meta = (uint32_t)kVarQuad << 22;
+        uint8_t* area = reinterpret_cast<uint8_t*>(&G) + 8;
+        const int nseg = 2 + nW + 2 * rb + 1;
+        size_t q = 0;
+        for (int sgi = 0; sgi <= nseg; ++sgi) {
+          while (q < pats.size() && seg_of(pats[q].zt) < sgi) ++q;
+          area[sgi] = (uint8_t)q;
+        }
+        sg.pats = pats;
+        P.n_quad++;
+        subs.push_back(std::move(sg));
+        continue;
+      }
+    }
     // sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 2047 patterns
     // per class.  Patterns are in class order, so cut greedily.
     size_t p = 0;
@@ -478,6 +554,10 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       if (has_im) P.has_im = true;
       if (flat) P.n_flat++;
       if (sg.var != kVarGeneral) P.n_fast++;
+      else {
+        P.n_general++;
+        P.n_general_patterns += count;
+      }
       sg.pats.assign(pats.begin() + p, pats.begin() + q);
       subs.push_back(std::move(sg));
       p = q;
@@ -489,63 +569,110 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     if (a.xlo != b.xlo) return a.xlo < b.xlo;
     return a.var < b.var;
   });
-  // chunks: consecutive sub-groups up to the staging capacity; a bundle cut by a chunk boundary
-  // simply becomes two bundle records
+  // runs of equal (remote, xlo) = bundles
+  struct Run { size_t s0, s1; int np, nq; };
+  std::vector<Run> runs;
+  const int qd = quad_table_doubles(P.L, rb);
+  for (size_t si = 0; si < subs.size();) {
+    size_t se = si;
+    int np = 0, nq = 0;
+    while (se < subs.size() && se - si < 255 && subs[se].remote == subs[si].remote && subs[se].xlo == subs[si].xlo &&
+           np + (int)subs[se].pats.size() <= kPatChunk && (int)(se - si) < kGrpChunk &&
+           (nq + (subs[se].var == kVarQuad ? 1 : 0)) * qd <= kQuadDoubles) {
+      np += (int)subs[se].pats.size();
+      nq += subs[se].var == kVarQuad ? 1 : 0;
+      ++se;
+    }
+    runs.push_back({si, se, np, nq});
+    si = se;
+  }
+  // chunks: consecutive runs up to the staging capacity.  Inside a chunk the singles (a local fast
+  // group alone in its run) come first, sorted by (im, xr); the other runs follow with a bundle record each
   P.pat_tptr.push_back(0);
-  size_t s0 = 0;
+  size_t r0 = 0;
   int g0 = 0, p0 = 0;
-  while (s0 < subs.size()) {
-    size_t s1 = s0;
-    int np = 0;
-    while (s1 < subs.size() && (int)(s1 - s0) < kGrpChunk && np + (int)subs[s1].pats.size() <= kPatChunk) {
-      np += (int)subs[s1].pats.size();
-      ++s1;
+  while (r0 < runs.size()) {
+    size_t r1 = r0;
+    int np = 0, ng = 0, nqc = 0;
+    while (r1 < runs.size() && ng + (int)(runs[r1].s1 - runs[r1].s0) <= kGrpChunk && np + runs[r1].np <= kPatChunk &&
+           (nqc + runs[r1].nq) * qd <= kQuadDoubles) {
+      np += runs[r1].np;
+      ng += (int)(runs[r1].s1 - runs[r1].s0);
+      nqc += runs[r1].nq;
+      ++r1;
     }
     ChunkRec cr;
     std::memset(&cr, 0, sizeof(cr));
     cr.b0 = (int32_t)P.bundles.size();
-    int pl = 0;
-    for (size_t si = s0; si < s1;) {
-      size_t se = si;
-      while (se < s1 && se - si < 255 && subs[se].remote == subs[si].remote && subs[se].xlo == subs[si].xlo) ++se;
-      BundleRec B;
-      const uint32_t xo = (subs[si].G.xt & 0x7fffffffu) & ~reg_tmask;
-      B.xo = xo | (subs[si].remote ? 0x80000000u : 0u);
-      uint32_t hbit = 0;
-      if (!subs[si].remote && xo != 0u) {
-        const int msb = 31 - __builtin_clz(xo);
-        if (msb >= kRegBitLo + rb) hbit = (uint32_t)(msb + 1);
+    auto s_index = [&](const SubGroup& sg) { return (int)((sg.G.meta >> 19) & 1u) * NA + (sg.var & (NA - 1)); };
+    std::vector<size_t> singles, multi;
+    for (size_t r = r0; r < r1; ++r) {
+      const SubGroup& sg = subs[runs[r].s0];
+      if (runs[r].s1 - runs[r].s0 == 1 && !sg.remote && sg.var != kVarGeneral) singles.push_back(r);
+      else multi.push_back(r);
+    }
+    std::stable_sort(singles.begin(), singles.end(), [&](size_t a, size_t b) {
+      return s_index(subs[runs[a].s0]) < s_index(subs[runs[b].s0]);
+    });
+    int pl = 0, gl = 0;
+    int nq_emitted = 0;
+    auto emit_group = [&](SubGroup& sg, uint32_t hbit) {
+      sg.G.meta |= (uint32_t)pl | (hbit << 28);
+      const bool is_quad = sg.var == kVarQuad;
+      if (is_quad) {
+        const uint16_t off = (uint16_t)(nq_emitted * qd);
+        std::memcpy(reinterpret_cast<uint8_t*>(&sg.G) + 30, &off, 2);
+        ++nq_emitted;
       }
-      B.meta = (uint32_t)(se - si) | (hbit << 8) | ((uint32_t)(si - s0) << 16);
+      for (size_t j = 0; j < sg.pats.size(); ++j) {
+        // bit 15 of the stored pattern marks patterns of a Hermitian-paired bundle (doubled by the
+        // fold of the Hermitian expectation kernels, masked off by every fold)
+        P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | (hbit ? 0x8000u : 0u)));
+        P.pat_inl.push_back(j < 2 && !is_quad ? (uint16_t)(gl * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
+        for (int t : sg.pats[j].terms) {
+          P.term_zb.push_back(comp[t].zl & ~S);
+          P.term_val.push_back(comp[t].val);
+        }
+        P.pat_tptr.push_back((uint32_t)P.term_val.size());
+        ++pl;
+      }
+      P.groups.push_back(sg.G);
+      ++gl;
+    };
+    auto hbit_of = [&](const SubGroup& sg) -> uint32_t {
+      const uint32_t xo = (sg.G.xt & 0x7fffffffu) & ~reg_tmask;
+      if (sg.remote || xo == 0u) return 0u;
+      const int msb = 31 - __builtin_clz(xo);
+      return msb >= kRegBitLo + rb ? (uint32_t)(msb + 1) : 0u;
+    };
+    for (size_t r : singles) {
+      SubGroup& sg = subs[runs[r].s0];
+      cr.s_cnt[s_index(sg)]++;
+      emit_group(sg, hbit_of(sg));
+    }
+    cr.ns = (uint16_t)singles.size();
+    P.n_singles += (int64_t)singles.size();
+    for (size_t r : multi) {
+      const size_t si = runs[r].s0, se = runs[r].s1;
+      BundleRec B;
+      const uint32_t hbit = hbit_of(subs[si]);
+      B.xo = ((subs[si].G.xt & 0x7fffffffu) & ~reg_tmask) | (subs[si].remote ? 0x80000000u : 0u);
+      B.meta = (uint32_t)(se - si) | (hbit << 8) | ((uint32_t)gl << 16);
       B.xlo = subs[si].xlo;
       P.bundles.push_back(B);
-      for (; si < se; ++si) {
-        SubGroup& sg = subs[si];
-        sg.G.meta |= (uint32_t)pl | (hbit << 28);
-        for (size_t j = 0; j < sg.pats.size(); ++j) {
-          // bit 15 of the stored pattern marks patterns of a Hermitian-paired bundle (doubled by the
-          // fold of the Hermitian expectation kernels, masked off by every fold)
-          P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | (hbit ? 0x8000u : 0u)));
-          P.pat_inl.push_back(j < 2 ? (uint16_t)((si - s0) * 2 + sg.slot_of[j]) : (uint16_t)0xffff);
-          for (int t : sg.pats[j].terms) {
-            P.term_zb.push_back(comp[t].zl & ~S);
-            P.term_val.push_back(comp[t].val);
-          }
-          P.pat_tptr.push_back((uint32_t)P.term_val.size());
-          ++pl;
-        }
-        P.groups.push_back(sg.G);
-      }
+      if (subs[si].remote) P.n_remote_bundles++;
+      for (size_t q = si; q < se; ++q) emit_group(subs[q], hbit);
     }
     cr.g0 = g0;
-    cr.ng = (int32_t)(s1 - s0);
+    cr.ng = gl;
     cr.p0 = p0;
-    cr.np = np;
+    cr.np = pl;
     cr.nb = (int32_t)P.bundles.size() - cr.b0;
+    cr.nq = (uint16_t)nq_emitted;
     P.chunks.push_back(cr);
-    g0 += (int)(s1 - s0);
-    p0 += np;
-    s0 = s1;
+    g0 += gl;
+    p0 += pl;
+    r0 = r1;
   }
   return P;
 }

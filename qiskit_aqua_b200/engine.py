@@ -131,6 +131,21 @@ class PauliSumEngine:
         return {'free_mask': fm.value, 'n_groups': ng.value, 'n_remote_groups': nr.value,
                 'n_patterns': npat.value}
 
+    def plan_floors(self, store=True):
+        """Lower bounds of one H.psi on this rank from the plan: dict(dram_bytes, smem_wavefronts,
+        group_records, partner_load_sets) (psum_plan_floors)."""
+        out = (C.c_double * 4)()
+        check(lib().psum_plan_floors(self._h, 1 if store else 0, out))
+        return {'dram_bytes': out[0], 'smem_wavefronts': out[1], 'group_records': int(out[2]),
+                'partner_load_sets': int(out[3])}
+
+    def exchange_stats(self):
+        """(exchanges, bytes per exchange, ms on the communication stream, span ms) of the last sharded
+        call made with option profile_exchange = 1."""
+        out = (C.c_double * 4)()
+        check(lib().psum_exchange_stats(self._h, out))
+        return [float(v) for v in out]
+
     @property
     def n_local_amps(self):
         return 1 << (self.num_qubits - (self.world.bit_length() - 1))

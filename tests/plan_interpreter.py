@@ -19,8 +19,8 @@ GROUP_DT = np.dtype([('xt', '<u4'), ('meta', '<u4'), ('zt0', '<u4'), ('zt1', '<u
                      ('cf1', '<f8'), ('xl', '<u8'), ('ent', '<u2', (4,))])
 BUNDLE_DT = np.dtype([('xo', '<u4'), ('meta', '<u4'), ('xlo', '<u8')])
 CHUNK_DT = np.dtype([('g0', '<i4'), ('ng', '<i4'), ('p0', '<i4'), ('np', '<i4'), ('b0', '<i4'), ('nb', '<i4'),
-                     ('pad', '<i4', (2,))])
-assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 32 and BUNDLE_DT.itemsize == 16
+                     ('ns', '<u2'), ('pad0', '<u2'), ('pad1', '<u4'), ('s_cnt', 'u1', (32,))])
+assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 64 and BUNDLE_DT.itemsize == 16
 VAR_GENERAL = 63
 
 
@@ -114,76 +114,92 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                 inl = int(ps['pat_inl'][gp])
                 if inl != 0xffff:
                     grp[inl >> 1]['cf1' if inl & 1 else 'cf0'] = v
-            seen = 0
+            def member(G, g, xo, remote, hbit, xlo):
+                """Contribution of group record G whose bundle has (xo, remote, hbit, xlo)."""
+                meta = int(G['meta'])
+                xt = int(G['xt']) & 0x7fffffff
+                xr = (xt >> 5) & (NA - 1)
+                var = (meta >> 22) & 63
+                k = reg ^ np.uint64(xr)                                   # pv[r ^ xr]
+                if remote:
+                    roff = _deposit(k, ps['fbit'][5:5 + rb])
+                    pv = src[(idx0 ^ np.uint64(xlo)) | roff]
+                else:
+                    pv = tile[(t0 ^ np.uint64(xo)) | (k << np.uint64(5))]
+                if check:
+                    assert int(G['xt']) >> 31 == remote and (meta >> 28) == hbit
+                    assert int(G['xl']) & ~regq == xlo
+                    assert np.array_equal(pv, src[idx ^ np.uint64(G['xl'])])
+                    if not remote:
+                        assert xt & ~int(regmask) == xo
+                        assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
+                # general evaluation from the class entry lists (every group carries them)
+                p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
+                D = np.zeros(1 << L, dtype=np.complex128)
+                any_im = False
+                for e in range(nent):
+                    ent = int(G['ent'][e])
+                    cnt, cls = ent & 0x7ff, ent >> 11
+                    sacc = np.zeros(1 << L)
+                    for j in range(cnt):
+                        if check:                   # class == register bits of the z-pattern
+                            assert (int(zt[p + j]) >> 5) & (NA - 1) == cls & (NA - 1)
+                        sacc += cf[p + j] * _sign(t0 & zt[p + j])
+                    p += cnt
+                    any_im |= cls >= NA
+                    D += (1j if cls >= NA else 1.0) * sacc * _sign(reg & np.uint64(cls & (NA - 1)))
+                if check:
+                    assert bool(flat) == (nent == 1 and int(G['ent'][0]) >> 11 == 0)
+                    assert bool((meta >> 20) & 1) == any_im and (ps['has_im'] or not any_im)
+                if var != VAR_GENERAL:
+                    # fast member: two inline slots, compile-time sign pattern
+                    im1 = (meta >> 19) & 1
+                    assert var < 2 * NA and bool(im1) == any_im and (var & (NA - 1)) == xr
+                    s0 = G['cf0'] * _sign(t0 & np.uint64(G['zt0']))
+                    s1 = G['cf1'] * _sign(t0 & np.uint64(G['zt1'])) * (1j if im1 else 1.0)
+                    Df = s0 + s1 if var < NA else s0 + s1 * _sign(reg & np.uint64(xr))
+                    if check:
+                        assert np.allclose(Df, D, rtol=0, atol=1e-13 * (1.0 + np.abs(D).max()))
+                    D = Df.astype(np.complex128)
+                elif check:
+                    assert not (meta >> 19) & 1
+                contrib = D * pv
+                if herm and hbit:
+                    contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
+                return contrib
+
+            def hbit_check(hbit, xo, remote):
+                if hbit:
+                    assert not remote and xo and hbit - 1 >= 5 + rb and (xo >> (hbit - 1)) == 1
+                else:
+                    assert remote or xo == 0 or xo.bit_length() - 1 < 5 + rb
+
+            # singles: sorted by s = im*NA + xr, no bundle record
+            ns = int(ch['ns'])
+            g = 0
+            for sidx in range(32):
+                for _ in range(int(ch['s_cnt'][sidx])):
+                    G = grp[g]
+                    meta = int(G['meta'])
+                    xt = int(G['xt'])
+                    if check:
+                        assert sidx < 2 * NA and (ps['has_im'] or sidx < NA)
+                        assert xt >> 31 == 0 and ((meta >> 22) & 63) != VAR_GENERAL
+                        assert (xt >> 5) & (NA - 1) == sidx & (NA - 1) and (meta >> 19) & 1 == sidx // NA
+                        hbit_check(meta >> 28, xt & ~int(regmask), 0)
+                    acc += member(G, g, xt & ~int(regmask), 0, meta >> 28, int(G['xl']) & ~regq)
+                    g += 1
+            assert g == ns
+            seen = ns
             for B in bundles[int(ch['b0']):int(ch['b0']) + int(ch['nb'])]:
                 xo, remote = int(B['xo']) & 0x7fffffff, int(B['xo']) >> 31
                 nmem, hbit, first = int(B['meta']) & 0xff, (int(B['meta']) >> 8) & 0xff, int(B['meta']) >> 16
                 if check:
                     assert first == seen and nmem >= 1 and xo & int(regmask) == 0 and int(B['xlo']) & regq == 0
-                    if hbit:
-                        assert not remote and xo and hbit - 1 >= 5 + rb and (xo >> (hbit - 1)) == 1
-                    else:
-                        assert remote or xo == 0 or xo.bit_length() - 1 < 5 + rb
+                    hbit_check(hbit, xo, remote)
                 seen += nmem
-                # the bundle's partner set: pvk[k] for a thread = tile[(t0 ^ xo) + (k << 5)]
                 for g in range(first, first + nmem):
-                    G = grp[g]
-                    meta = int(G['meta'])
-                    xt = int(G['xt']) & 0x7fffffff
-                    xr = (xt >> 5) & (NA - 1)
-                    var = (meta >> 22) & 63
-                    k = reg ^ np.uint64(xr)                                   # pv[r ^ xr]
-                    if remote:
-                        roff = _deposit(k, ps['fbit'][5:5 + rb])
-                        pv = src[(idx0 ^ np.uint64(B['xlo'])) | roff]
-                    else:
-                        pv = tile[(t0 ^ np.uint64(xo)) | (k << np.uint64(5))]
-                    if check:
-                        assert int(G['xt']) >> 31 == remote and (meta >> 28) == hbit
-                        assert int(G['xl']) & ~regq == int(B['xlo'])
-                        assert np.array_equal(pv, src[idx ^ np.uint64(G['xl'])])
-                        if not remote:
-                            assert xt & ~int(regmask) == xo
-                            assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
-                    # general evaluation from the class entry lists (every group carries them)
-                    p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
-                    D = np.zeros(1 << L, dtype=np.complex128)
-                    any_im = False
-                    for e in range(nent):
-                        ent = int(G['ent'][e])
-                        cnt, cls = ent & 0x7ff, ent >> 11
-                        sacc = np.zeros(1 << L)
-                        for j in range(cnt):
-                            if check:                   # class == register bits of the z-pattern
-                                assert (int(zt[p + j]) >> 5) & (NA - 1) == cls & (NA - 1)
-                            sacc += cf[p + j] * _sign(t0 & zt[p + j])
-                        p += cnt
-                        any_im |= cls >= NA
-                        D += (1j if cls >= NA else 1.0) * sacc * _sign(reg & np.uint64(cls & (NA - 1)))
-                    if check:
-                        assert bool(flat) == (nent == 1 and int(G['ent'][0]) >> 11 == 0)
-                        assert bool((meta >> 20) & 1) == any_im and (ps['has_im'] or not any_im)
-                    if var != VAR_GENERAL:
-                        # fast member: two inline slots, compile-time sign pattern
-                        im1 = (meta >> 19) & 1
-                        assert var < 2 * NA and bool(im1) == any_im
-                        s0 = G['cf0'] * _sign(t0 & np.uint64(G['zt0']))
-                        s1 = G['cf1'] * _sign(t0 & np.uint64(G['zt1'])) * (1j if im1 else 1.0)
-                        if var < NA:
-                            assert var == xr
-                            Df = s0 + s1
-                        else:
-                            assert var - NA == xr
-                            Df = s0 + s1 * _sign(reg & np.uint64(xr))
-                        if check:
-                            assert np.allclose(Df, D, rtol=0, atol=1e-13 * (1.0 + np.abs(D).max()))
-                        D = Df.astype(np.complex128)
-                    elif check:
-                        assert not (meta >> 19) & 1
-                    contrib = D * pv
-                    if herm and hbit:
-                        contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
-                    acc += contrib
+                    acc += member(grp[g], g, xo, remote, hbit, int(B['xlo']))
             assert seen == ng
         if y is not None:
             y[idx] += acc
