@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument('--tile-bits', type=int, default=0)
     ap.add_argument('--low-bits', type=int, default=0)
     ap.add_argument('--reg-bits', type=int, default=0)
+    ap.add_argument('--cta-mode', type=int, default=-1)
     return ap.parse_args()
 
 
@@ -272,6 +273,8 @@ def main():
         opts['low_bits'] = args.low_bits
     if args.reg_bits:
         opts['reg_bits'] = args.reg_bits
+    if args.cta_mode >= 0:
+        opts['cta_mode'] = args.cta_mode
     eng = PauliSumEngine(n_total, x, z, y, c, opts)
     recv = None
     if world > 1:

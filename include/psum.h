@@ -54,6 +54,9 @@ int psum_destroy(psum_handle_t h);
  * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover";
  * "reg_bits" (3 default | 4): amplitudes per thread = 2^reg_bits.  x-groups whose masks differ only
  * in the register qubits of a pass share one set of partner loads (a "bundle");
+ * "cta_mode" (0 auto | 1 two CTAs per SM | 2 one big CTA per SM): a pass with quadratic groups or more
+ * than one chunk runs as one CTA per SM with twice the threads and large staging capacities;
+ * "copy_threads" (0 auto): host threads that fill the pinned bounce ring for pageable input;
  * "herm_pairing" (1 default): psum_expect of a Hermitian operator evaluates each amplitude pair
  * (i, i^x) once and doubles it (the imaginary part of the result is then exactly the rounding
  * noise of a real quantity); 0 forces the generic path.
@@ -65,7 +68,8 @@ int psum_set_option(psum_handle_t h, const char* key, int64_t value);
  * global memory ("remote") [5]=is_hermitian [6]=is_diagonal [7]=local qubits [8]=sum of patterns
  * [9]=component terms [10]=tile_bits [11]=distinct non-zero global x-parts [12]=flat groups
  * [13]=group records (x-groups after class splitting) [14]=group records served by a fast variant
- * [15]=bundles (partner load sets; <= group records) */
+ * [15]=partner load sets (bundles + singles; <= group records) [16]=quadratic groups (separable
+ * table evaluation) */
 int psum_info(psum_handle_t h, int64_t* info, int n_info);
 /* Free-bit set (bit mask over local qubits) and group count of pass p of global part g. */
 int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* n_groups,
@@ -74,12 +78,14 @@ int psum_pass_info(psum_handle_t h, int g, int p, uint64_t* free_mask, int64_t* 
  * global part g exactly as the kernels read them, so the planner can be verified without a GPU
  * (tests/plan_interpreter.py).  counts: [0]=group records (48 B each) [1]=patterns [2]=component
  * terms [3]=chunks (32 B each) [4]=tile bits L [5]=non-free local bits [6]=has imaginary patterns
- * [7]=highest local qubit the pass combines [8]=bundle records (16 B each) [9]=register bits RB.
- * Any buffer may be NULL (call once for the counts); pat_tptr holds patterns+1 entries.  Record
- * layouts: qiskit_aqua_b200/csrc/psum_plan.h. */
-int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[10], void* groups,
+ * [7]=highest local qubit the pass combines [8]=bundle records (16 B each) [9]=register bits RB
+ * [10]=quadratic groups (entries of quad_idx) [11]=1 if the pass runs as one big CTA per SM.
+ * Any buffer may be NULL (call once for the counts); pat_tptr holds patterns+1 entries; chunk
+ * records are 64 B.  Record layouts: qiskit_aqua_b200/csrc/psum_plan.h. */
+int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[12], void* groups,
                      uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
-                     double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles);
+                     double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles,
+                     uint16_t* quad_idx);
 
 /* Lower bounds of one H.psi on this rank computed from the plan (host only): out[0] = DRAM bytes
  * (store != 0: y is written), out[1] = shared-memory wavefronts, out[2] = group records, out[3] =

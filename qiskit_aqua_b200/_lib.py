@@ -23,7 +23,7 @@ SIGNATURES = {
     'psum_set_option': (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     'psum_info': (C.c_int, [_vp, _i64p, C.c_int]),
     'psum_pass_info': (C.c_int, [_vp, C.c_int, C.c_int, _u64p, _i64p, _i64p, _i64p]),
-    'psum_plan_export': (C.c_int, [_vp, C.c_int, C.c_int, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'psum_plan_export': (C.c_int, [_vp, C.c_int, C.c_int, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'psum_plan_floors': (C.c_int, [_vp, C.c_int, _dp]),
     'psum_exchange_stats': (C.c_int, [_vp, _dp]),
     'psum_apply': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),

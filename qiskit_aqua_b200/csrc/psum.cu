@@ -189,7 +189,7 @@ static int plan(psum_handle_s* h) {
   return PSUM_OK;
 }
 
-static size_t pass_smem_bytes(int L) { return pass_smem_bytes_c(L); }
+static size_t pass_smem_bytes(int L, bool big, int quad_cap) { return pass_smem_bytes_c(L, big, quad_cap); }
 
 template <typename T>
 static T* arena_put(char* base, size_t& off, const std::vector<T>& v, std::vector<char>& host) {
@@ -255,10 +255,17 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
         dp.rb = ph.rb;
         dp.has_im = ph.has_im;
         dp.hi_bit = ph.hi_bit;
-        dp.smem = pass_smem_bytes(ph.L);
-        // 2^RB amplitudes per thread; 2^13 tiles run one CTA per SM, smaller ones two
-        dp.threads = (ph.L >= 13 ? 4096 : 2048) >> ph.rb;
-        int per_sm = dp.smem > 113 * 1024 ? 1 : 2;
+        dp.params.quad_idx = arena_put(base, off, ph.quad_idx, host);
+        // 2^RB amplitudes per thread; 2^13 tiles and "big" passes run one CTA per SM, the rest two.
+        // The kernel configuration (threads << RB >= 4096) fixes the static staging capacities.
+        const bool big_cfg = ph.L >= 13 || ph.caps.big;
+        dp.threads = (big_cfg ? 4096 : 2048) >> ph.rb;
+        // quad arena: what the plan needs, at least one table set so that the pointer stays in bounds
+        int max_nq = 0;
+        for (const ChunkRec& cr : ph.chunks) max_nq = std::max<int>(max_nq, cr.nq);
+        dp.params.quad_cap = max_nq * quad_table_doubles(ph.L, ph.rb);
+        dp.smem = pass_smem_bytes(ph.L, big_cfg, dp.params.quad_cap);
+        int per_sm = (dp.smem > 113 * 1024 || big_cfg) ? 1 : 2;
         dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
         pass_partials += dp.grid;
         D.passes.push_back(dp);
@@ -297,7 +304,7 @@ static int upload(psum_handle_s* h) {
   static bool attr_done_dev[64] = {false};  // function attributes are per device
   bool& attr_done = attr_done_dev[h->device >= 0 && h->device < 64 ? h->device : 0];
   if (!attr_done) {
-    const int max_smem = (int)pass_smem_bytes(kMaxTileBits);
+    const int max_smem = 227 * 1024;
     CUDA_TRY(kpass_set_smem_3_256(max_smem));
     CUDA_TRY(kpass_set_smem_3_512(max_smem));
     CUDA_TRY(kpass_set_smem_4_128(max_smem));
@@ -384,6 +391,9 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "reg_bits") {
     if (value != 3 && value != 4) return fail(PSUM_ERR_INVALID, "reg_bits must be 3 or 4");
     h->opt.reg_bits = (int)value;
+  } else if (k == "cta_mode") {
+    if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "cta_mode must be 0 (auto), 1 (two CTAs per SM) or 2 (one big CTA)");
+    h->opt.cta_mode = (int)value;
   } else if (k == "late_bits") {
     if (value < 0 || value > 8) return fail(PSUM_ERR_INVALID, "late_bits must be 0..8");
     h->opt.late_bits = (int)value;
@@ -415,7 +425,8 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
 extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
   if (!h || !info) return fail(PSUM_ERR_INVALID, "null argument");
   if (!h->planned) PS_TRY(plan(h));
-  int64_t v[16] = {0};
+  int64_t v[17] = {0};
+  int64_t v16 = 0;
   v[0] = h->n;
   v[1] = (int64_t)h->terms.size();
   {
@@ -433,6 +444,7 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
       v[12] += ps.n_flat;
       v[14] += ps.n_fast;
       v[15] += (int64_t)ps.bundles.size() + ps.n_singles;
+      v16 += ps.n_quad;
       v[13] += (int64_t)ps.groups.size();
       v[10] = ps.L;
     }
@@ -443,7 +455,8 @@ extern "C" int psum_info(psum_handle_t h, int64_t* info, int n_info) {
   v[6] = h->diagonal;
   v[7] = h->n_loc;
   v[11] = gparts;
-  for (int i = 0; i < n_info && i < 16; ++i) info[i] = v[i];
+  v[16] = v16;
+  for (int i = 0; i < n_info && i < 17; ++i) info[i] = v[i];
   return PSUM_OK;
 }
 
@@ -493,6 +506,10 @@ extern "C" int psum_plan_floors(psum_handle_t h, int store, double out[4]) {
       dram += 16.0 * N * (1.0 + (store ? (first ? 1.0 : 2.0) : 0.0) + (double)ps.n_remote_bundles);
       wf += warp_rounds * (4.0 * na * local_sets + 2.0 * (double)ps.n_fast + 3.0 * (double)ps.n_general +
                            (double)ps.n_general_patterns + (double)ps.bundles.size());
+      {  // quadratic member: 2 record reads, (1 + nW + RB) lane-table reads of 2 wavefronts, the rest broadcast
+        const int nW = ps.L - kRegBitLo - ps.rb;
+        wf += warp_rounds * (double)ps.n_quad * (2.0 + 2.0 * (1 + nW + ps.rb) + 1.0 + ps.rb + 0.5 * ps.rb * (ps.rb - 1));
+      }
       wf += N * 16.0 / 128.0;
       ngr += (double)ps.groups.size();
       nsets += (double)ps.n_singles + (double)ps.bundles.size();
@@ -508,9 +525,10 @@ extern "C" int psum_plan_floors(psum_handle_t h, int store, double out[4]) {
 
 // Plan introspection (host only): hands out the device-facing arrays of one pass exactly as the
 // kernels read them, so that the planner can be checked without a device (tests/plan_interpreter.py).
-extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[10], void* groups,
+extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[12], void* groups,
                                 uint16_t* pat_zt, uint16_t* pat_inl, uint32_t* pat_tptr, uint64_t* term_zb,
-                                double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles) {
+                                double* term_val, void* chunks, uint8_t fbit[16], uint8_t nbit[64], void* bundles,
+                                uint16_t* quad_idx) {
   if (!h || !counts) return fail(PSUM_ERR_INVALID, "null argument");
   if (!h->planned) PS_TRY(plan(h));
   PartHost* P = find_part(h, g);
@@ -526,6 +544,9 @@ extern "C" int psum_plan_export(psum_handle_t h, int g, int p, int64_t counts[10
   counts[7] = ps.hi_bit;
   counts[8] = (int64_t)ps.bundles.size();
   counts[9] = ps.rb;
+  counts[10] = (int64_t)ps.quad_idx.size();
+  counts[11] = ps.caps.big ? 1 : 0;
+  if (quad_idx) memcpy(quad_idx, ps.quad_idx.data(), ps.quad_idx.size() * sizeof(uint16_t));
   if (groups) memcpy(groups, ps.groups.data(), ps.groups.size() * sizeof(GroupRec));
   if (bundles) memcpy(bundles, ps.bundles.data(), ps.bundles.size() * sizeof(BundleRec));
   if (pat_zt) memcpy(pat_zt, ps.pat_zt.data(), ps.pat_zt.size() * sizeof(uint16_t));
@@ -816,6 +837,27 @@ extern "C" int psum_diag(psum_handle_t h, double* d_dev, psum_stream_t stream) {
   // the rank sign of the global z-part is already folded into the coefficients.
   k_diag<<<D0->grid_stream, kThreads, 0, (cudaStream_t)stream>>>(d_dev, D0->sterms, D0->nst,
                                                                 n_local_amps(h), 0);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+// Dense matrix of the operator on the device (row-major 2^n x 2^n complex128): the matrix the
+// reference builds with to_matrix() (operator_base / list_op.py:320-329).  Small n only.
+extern "C" int psum_to_dense(psum_handle_t h, void* mat_dev, psum_stream_t stream) {
+  if (!h || !mat_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle is sharded");
+  if (h->n > 14) return fail(PSUM_ERR_INVALID, "dense matrix of %d qubits refused (2^%d entries)", h->n, 2 * h->n);
+  if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  PS_TRY(upload(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t N = n_local_amps(h);
+  CUDA_TRY(cudaMemsetAsync(mat_dev, 0, N * N * sizeof(double2), st));
+  for (const DevPart& D : h->dparts) {
+    if (D.g != 0 || D.nsg == 0) continue;
+    const uint64_t total = N * (uint64_t)D.nsg;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((total + kThreads - 1) / kThreads, (uint64_t)h->num_sms * 16));
+    k_to_dense<<<grid, kThreads, 0, st>>>((double2*)mat_dev, D.sgroups, D.nsg, D.sterms, N);
+  }
   CUDA_TRY(cudaGetLastError());
   return PSUM_OK;
 }

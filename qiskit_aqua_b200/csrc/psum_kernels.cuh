@@ -37,10 +37,12 @@ struct PassParams {
   const uint64_t* term_zb;
   const double* term_val;
   const ChunkRec* chunks;
+  const uint16_t* quad_idx;
   int nchunks;
   int L;
   int n_nonfree;
   int accumulate;
+  int quad_cap;   // doubles of the quad-table arena behind the tile
   uint64_t ntiles;
   uint64_t tile_begin, tile_end;  // tile range of this launch (whole pass: 0 .. ntiles)
   uint64_t roff[16];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
@@ -49,9 +51,14 @@ struct PassParams {
 };
 
 // shared memory of one k_pass CTA (bytes), L tile bits
-__host__ __device__ constexpr size_t pass_smem_bytes_c(int L) {
-  return ((size_t)16 << L) + sizeof(PatRec) * kPatChunk + 8 * 64 + sizeof(GroupRec) * (kGrpChunk + 1) +
-         sizeof(BundleRec) * (kGrpChunk + 1) + 16 * 16 + 8 * 9 * 64;
+// layout: [offHi 64 u64][red 16 double2][baseT 9*64 u64][group records][bundle records][patterns] at
+// compile-time offsets (big = one CTA per SM), then the tile (2^L amplitudes), then the quad arena
+__host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
+  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
+         sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
+}
+__host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap) {
+  return pass_static_bytes_c(big) + ((size_t)16 << L) + 8 * (size_t)quad_cap;
 }
 
 __device__ __forceinline__ double flip_sign(double v, int s) {
@@ -188,14 +195,18 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = P.L;
   const uint32_t tile_amps = 1u << L;
-  double2* tile = reinterpret_cast<double2*>(smem_raw);
-  PatRec* pat = reinterpret_cast<PatRec*>(tile + tile_amps);
-  uint64_t* offHi = reinterpret_cast<uint64_t*>(pat + kPatChunk);
-  uint4* grp4 = reinterpret_cast<uint4*>(offHi + 64);               // 3 x uint4 per group record
-  uint4* bun4 = grp4 + 3 * (kGrpChunk + 1);                         // 1 x uint4 per bundle record
-  double2* red = reinterpret_cast<double2*>(bun4 + (kGrpChunk + 1));
+  constexpr bool BIG = (NT << RB) >= 4096;
+  constexpr int PCAP = BIG ? kPatCapBig : kPatCapSmall, GCAP = BIG ? kGrpCapBig : kGrpCapSmall;
+  uint64_t* offHi = reinterpret_cast<uint64_t*>(smem_raw);
+  double2* red = reinterpret_cast<double2*>(offHi + 64);
   uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
+  uint4* grp4 = reinterpret_cast<uint4*>(baseT + 9 * 64);   // 3 x uint4 per group record
+  uint4* bun4 = grp4 + 3 * (GCAP + 1);                      // 1 x uint4 per bundle record
+  PatRec* pat = reinterpret_cast<PatRec*>(bun4 + (GCAP + 1));
+  double2* tile = reinterpret_cast<double2*>(pat + PCAP);
+  double* qtab = reinterpret_cast<double*>(tile + tile_amps);   // tables of the chunk's quadratic groups
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
+  const int nW = L - 5 - RB;                                 // warp/round tile bits
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -253,6 +264,50 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       const uint32_t inl = P.pat_inl[gp];
       if (inl != 0xffffu)
         reinterpret_cast<double*>(grp4 + 3 * (inl >> 1) + 1)[inl & 1u] = v;
+    }
+    if (ch.nq) {
+      // quadratic groups: rebuild the separable tables of this tile from the folded patterns.
+      // One task = one table of one group = the signed sum of one pattern segment (psum_plan.h) for
+      // every table index; a task runs on one warp, lane = table index, so the pattern loop is uniform.
+      __syncthreads();
+      const int nlt = 1 + nW + RB, ntab = nlt + 1 + RB + 1;
+      for (int task = warp; task < (int)ch.nq * ntab; task += NT / 32) {
+        const int qi = task / ntab, tb = task - qi * ntab;
+        const int g = (int)P.quad_idx[ch.q0 + qi];
+        const uint32_t meta = reinterpret_cast<const uint32_t*>(grp4 + 3 * g)[1];
+        const uint8_t* area = reinterpret_cast<const uint8_t*>(grp4 + 3 * g) + 8;
+        double* qt = qtab + (int)*reinterpret_cast<const uint16_t*>(area + 22);
+        const int pfirst = (int)(meta & 0xffffu);
+        int seg, dst, cnt;
+        uint32_t M;
+        bool filt = false;
+        if (tb < nlt) {                    // lane tables: T_L, C_j, TL_i
+          seg = tb == 0 ? 0 : tb + 1;
+          M = (uint32_t)lane;
+          dst = tb * 32 + lane;
+          cnt = 32;
+        } else if (tb < nlt + 1 + RB) {    // w tables: T_W, TW_i
+          const int t = tb - nlt;
+          seg = t == 0 ? 1 : 2 + nW + RB + (t - 1);
+          M = (uint32_t)lane << (5 + RB);
+          dst = nlt * 32 + (t << nW) + lane;
+          cnt = 1 << nW;
+        } else {                           // K[mask of two register bits]
+          seg = 2 + nW + 2 * RB;
+          M = 0u;
+          filt = true;
+          dst = nlt * 32 + ((1 + RB) << nW) + lane;
+          cnt = NA;
+        }
+        double v = 0.0;
+        const int pa = pfirst + (int)area[seg], pb = pfirst + (int)area[seg + 1];
+        for (int p = pa; p < pb; ++p) {
+          const uint4 rec = pat4[p];
+          const double c = __hiloint2double((int)(rec.y ^ ((uint32_t)__popc(rec.z & M) << 31)), (int)rec.x);
+          if (!filt || (int)((rec.z >> 5) & (uint32_t)(NA - 1)) == lane) v += c;
+        }
+        if (lane < cnt) qt[dst] = v;
+      }
     }
   };
 
@@ -326,26 +381,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           }
         }
         // ---- bundles: one set of partner amplitudes, a register permutation per member ----------
-        // The member records are consecutive over all bundles of the chunk: the next record (and
-        // the next bundle header) is fetched while the current member is being applied.
         {
-          int g = (int)ch.ns;
-          uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
-          uint4 B = bun4[0];
           for (int b = 0; b < ch.nb; ++b) {
-            const uint4 Bn = bun4[b + 1];
+            const uint4 B = bun4[b];
+            int g = (int)(B.y >> 16);
             const int gend = g + (int)(B.y & 0xffu);
-            bool skip = false;
             if (HERM) {  // partner half of a paired bundle (warp-uniform)
               const uint32_t hb = (B.y >> 8) & 0xffu;
-              skip = hb && ((t0 >> (hb - 1u)) & 1u);
-            }
-            if (skip) {
-              g = gend;
-              h0 = grp4[3 * g];
-              hc = grp4[3 * g + 1];
-              B = Bn;
-              continue;
+              if (hb && ((t0 >> (hb - 1u)) & 1u)) continue;
             }
             double2 pv[NA];
             if (!(B.x >> 31)) {
@@ -357,9 +400,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
               for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
             }
-            B = Bn;
             for (; g < gend; ++g) {
-              const uint4 n0 = grp4[3 * g + 3], nc = grp4[3 * g + 4];   // next member (or the overrun slot)
+              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
               const uint32_t var = (h0.y >> 22) & 63u;
               const uint32_t xr = (h0.x >> 5) & (uint32_t)(NA - 1);
               if (var < 2u * NA) {
@@ -382,6 +424,41 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                     PSUM_REP32(PSUM_FAST_CASE)
 #undef PSUM_FAST_CASE
                   }
+                }
+              } else if (var == (uint32_t)kVarQuad) {
+                // quadratic member: D from the separable tables of this tile
+                const double* qt = qtab + (hc.w >> 16);
+                const int w = (int)(t0 >> (5 + RB)), wsz = 1 << nW;
+                const double* qw = qt + (1 + nW + RB) * 32;
+                double v[NA];
+#pragma unroll
+                for (int m = 0; m < NA; ++m) v[m] = 0.0;
+                double a0 = qt[lane] + qw[w];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                  if (j < nW) a0 += flip_sign(qt[32 * (1 + j) + lane], (w >> j) & 1);
+                v[0] = a0;
+#pragma unroll
+                for (int i = 0; i < RB; ++i) v[1 << i] = qt[32 * (1 + nW + i) + lane] + qw[(1 + i) * wsz + w];
+#pragma unroll
+                for (int m = 0; m < NA; ++m)
+                  if (__popc(m) == 2) v[m] = qw[(1 + RB) * wsz + m];
+                // Walsh-Hadamard over the register bits: D[r] = sum_m (-1)^{popc(m & r)} v[m]
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+#pragma unroll
+                  for (int m = 0; m < NA; ++m) {
+                    if (!(m & (1 << i))) {
+                      const double a = v[m], b = v[m | (1 << i)];
+                      v[m] = a + b;
+                      v[m | (1 << i)] = a - b;
+                    }
+                  }
+                }
+                switch (xr) {
+#define PSUM_PERM_CASE(V) case V: perm_fma<NA, V, false, NA>(yacc, pv, v); break;
+                  PSUM_REP32(PSUM_PERM_CASE)
+#undef PSUM_PERM_CASE
                 }
               } else {
                 // general member: class entry lists
@@ -426,8 +503,6 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                   }
                 }
               }
-              h0 = n0;
-              hc = nc;
             }
           }
         }
@@ -495,6 +570,26 @@ k_stream(const double2* __restrict__ src, const double2* __restrict__ bra, doubl
   if (partial) {
     double2 tot = block_reduce(eacc, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  }
+}
+
+// dense matrix of the sum (row-major N x N, zero-initialised by the caller): H[i][i ^ x_g] = D_g(i).
+// One thread per (row, group).  Small n only (to_matrix / the k >= 2^n - 1 branch of the eigensolver).
+__global__ void __launch_bounds__(kThreads)
+k_to_dense(double2* __restrict__ H, const SimpleGroup* __restrict__ groups, int ngroups,
+           const SimpleTerm* __restrict__ terms, uint64_t n_amps) {
+  const uint64_t total = n_amps * (uint64_t)ngroups;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = e % n_amps;
+    const SimpleGroup G = groups[e / n_amps];
+    double dre = 0.0, dim = 0.0;
+    for (int t = G.t0; t < G.t0 + G.nt; ++t) {
+      const SimpleTerm T = terms[t];
+      const int s = __popcll(i & T.z) & 1;
+      dre += flip_sign(T.re, s);
+      dim += flip_sign(T.im, s);
+    }
+    H[i * n_amps + (i ^ G.xl)] = make_double2(dre, dim);
   }
 }
 

@@ -90,7 +90,7 @@ struct ChunkRec {  // 64 bytes
                    // bundle.  They need no bundle record and are sorted by s = im*NA + xr so that each
                    // (im, xr) runs its own straight-line loop with a compile-time register permutation
   uint16_t nq;     // quadratic groups in the chunk (their tables are rebuilt per tile)
-  uint32_t pad1;
+  uint32_t q0;     // their group indices (inside the chunk): quad_idx[q0 .. q0 + nq)
   uint8_t s_cnt[32];  // singles per s
 };
 static_assert(sizeof(ChunkRec) == 64, "ChunkRec layout");
@@ -128,9 +128,32 @@ inline int quad_table_doubles(int L, int rb) {
 constexpr int kPatChunk = PSUM_PAT_CHUNK;  // patterns staged in shared memory at a time
 constexpr int kGrpChunk = PSUM_GRP_CHUNK;  // groups staged in shared memory at a time
 
+// Staging capacities of one chunk.  A pass runs either as two CTAs per SM (tiles up to 2^12, the
+// small capacities, two rounds per tile) or as ONE big CTA per SM (twice the threads, one round
+// per tile up to 2^12, most of the SM's shared memory for the plan): dense passes -- many groups,
+// quadratic-group tables -- then fit one chunk, so the fold and the table build run once per tile.
+// The pattern / group capacities are compile-time constants of the kernel configuration (static
+// shared-memory offsets); only the quad arena, which sits behind the tile, has a run-time size.
+constexpr int kPatCapSmall = PSUM_PAT_CHUNK, kGrpCapSmall = PSUM_GRP_CHUNK;
+constexpr int kPatCapBig = 2048, kGrpCapBig = 192;   // <= 255 groups: per-(im, xr) single counters are bytes
+struct ChunkCaps {
+  int pat = kPatCapSmall, grp = kGrpCapSmall, quad = kQuadDoubles;
+  bool big = false;
+};
+inline ChunkCaps small_caps() { return ChunkCaps(); }
+inline ChunkCaps big_caps(int L) {   // the CTA's shared memory (tile + staging) must stay below 227 KB
+  ChunkCaps c;
+  c.pat = kPatCapBig;
+  c.grp = kGrpCapBig;
+  c.quad = L >= 13 ? 4096 : 8192;
+  c.big = true;
+  return c;
+}
+
 struct PassHost {
   int L = 0;                   // tile bits
   int rb = 3;                  // register bits (2^rb amplitudes per thread)
+  ChunkCaps caps;              // staging capacities this pass was chunked for (caps.big: one CTA per SM)
   uint64_t free_mask = 0;      // over local qubits
   uint8_t fbit[16] = {0};      // qubit of tile bit j: 0..4 lane bits, 5..5+rb-1 register bits, then warp/round
   bool has_im = false;         // any imaginary component pattern in this pass
@@ -138,6 +161,7 @@ struct PassHost {
   int64_t n_flat = 0;          // groups whose D is the same for all register amplitudes
   int64_t n_fast = 0;          // groups served by a fast variant (real, <= 2 inline patterns)
   std::vector<BundleRec> bundles;
+  std::vector<uint16_t> quad_idx;   // group index (inside its chunk) of every quadratic group
   int64_t n_singles = 0;       // fast groups alone in their bundle (no bundle record)
   int64_t n_remote_bundles = 0, n_general = 0, n_general_patterns = 0;   // for the cost model
   int64_t n_quad = 0;          // quadratic groups (table evaluation)
@@ -171,11 +195,13 @@ struct PartHost {  // all terms whose global x-part is g
 
 struct PlanOptions {
   int tile_bits = 12;
-  int low_bits = 4;
+  int low_bits = 3;    // lowest qubits always free: 2^3 amplitudes = one 128-byte line per run
   int min_cover = 3;
   int plan_tries = 8;  // randomised greedy restarts of the pass planner; the cheapest plan wins
   int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)
   int reg_bits = 3;    // 3: 8 amplitudes per thread, 256-thread CTAs; 4: 16 per thread, 128-thread CTAs
+  int cta_mode = 0;    // 0 auto (a pass that needs several chunks or holds quadratic groups runs as one
+                       // big CTA per SM), 1 always two CTAs per SM, 2 always one big CTA
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
 };
 
@@ -320,8 +346,10 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
 // Build the device-facing arrays of one pass.
 inline PassHost build_pass(const std::vector<CompTerm>& comp,
                            const std::vector<std::vector<int>>& terms_of_mask,
-                           const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc, int rb) {
+                           const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc, int rb,
+                           const ChunkCaps caps = ChunkCaps()) {
   PassHost P;
+  P.caps = caps;
   P.free_mask = pc.free_mask;
   P.L = popc64(pc.free_mask);
   P.rb = rb;
@@ -452,7 +480,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     }
     // quadratic group?  (all patterns real, at most two tile bits each)
     {
-      bool quad = (int)pats.size() >= kQuadMinPatterns && pats.size() <= 255 && quad_table_doubles(P.L, rb) <= kQuadDoubles;
+      bool quad = (int)pats.size() >= kQuadMinPatterns && pats.size() <= 255 && quad_table_doubles(P.L, rb) <= caps.quad;
       for (const PatTmp& pt : pats)
         if (pt.cls >= NA || __builtin_popcount(pt.zt) > 2) quad = false;
       if (quad) {
@@ -494,7 +522,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
         continue;
       }
     }
-    // sub-groups: each holds <= 4 non-empty classes, <= kPatChunk patterns and <= 2047 patterns
+    // sub-groups: each holds <= 4 non-empty classes, <= caps.pat patterns and <= 2047 patterns
     // per class.  Patterns are in class order, so cut greedily.
     size_t p = 0;
     while (p < pats.size()) {
@@ -508,7 +536,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       int count = 0, nent = 0;
       bool has_im = false;
       size_t q = p;
-      while (q < pats.size() && count < kPatChunk) {
+      while (q < pats.size() && count < caps.pat) {
         const int cls = pats[q].cls;
         if (nent == 0 || (G.ent[nent - 1] >> 11) != cls) {
           if (nent == 4) break;
@@ -577,8 +605,8 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     size_t se = si;
     int np = 0, nq = 0;
     while (se < subs.size() && se - si < 255 && subs[se].remote == subs[si].remote && subs[se].xlo == subs[si].xlo &&
-           np + (int)subs[se].pats.size() <= kPatChunk && (int)(se - si) < kGrpChunk &&
-           (nq + (subs[se].var == kVarQuad ? 1 : 0)) * qd <= kQuadDoubles) {
+           np + (int)subs[se].pats.size() <= caps.pat && (int)(se - si) < caps.grp &&
+           (nq + (subs[se].var == kVarQuad ? 1 : 0)) * qd <= caps.quad) {
       np += (int)subs[se].pats.size();
       nq += subs[se].var == kVarQuad ? 1 : 0;
       ++se;
@@ -594,8 +622,8 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
   while (r0 < runs.size()) {
     size_t r1 = r0;
     int np = 0, ng = 0, nqc = 0;
-    while (r1 < runs.size() && ng + (int)(runs[r1].s1 - runs[r1].s0) <= kGrpChunk && np + runs[r1].np <= kPatChunk &&
-           (nqc + runs[r1].nq) * qd <= kQuadDoubles) {
+    while (r1 < runs.size() && ng + (int)(runs[r1].s1 - runs[r1].s0) <= caps.grp && np + runs[r1].np <= caps.pat &&
+           (nqc + runs[r1].nq) * qd <= caps.quad) {
       np += runs[r1].np;
       ng += (int)(runs[r1].s1 - runs[r1].s0);
       nqc += runs[r1].nq;
@@ -604,6 +632,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     ChunkRec cr;
     std::memset(&cr, 0, sizeof(cr));
     cr.b0 = (int32_t)P.bundles.size();
+    cr.q0 = (uint32_t)P.quad_idx.size();
     auto s_index = [&](const SubGroup& sg) { return (int)((sg.G.meta >> 19) & 1u) * NA + (sg.var & (NA - 1)); };
     std::vector<size_t> singles, multi;
     for (size_t r = r0; r < r1; ++r) {
@@ -622,6 +651,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       if (is_quad) {
         const uint16_t off = (uint16_t)(nq_emitted * qd);
         std::memcpy(reinterpret_cast<uint8_t*>(&sg.G) + 30, &off, 2);
+        P.quad_idx.push_back((uint16_t)gl);
         ++nq_emitted;
       }
       for (size_t j = 0; j < sg.pats.size(); ++j) {
@@ -749,7 +779,17 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
           pcs.swap(cand);
         }
       }
-      for (auto& pc : pcs) P.passes.push_back(build_pass(P.comp, tom, masks, pc, n_loc, opt.reg_bits == 4 ? 4 : 3));
+      for (auto& pc : pcs) {
+        const int rb = opt.reg_bits == 4 ? 4 : 3;
+        // one big CTA needs a full round of 2^12 amplitudes: tiles of 2^11 always run as two CTAs
+        const int Lp = popc64(pc.free_mask);
+        const bool can_big = Lp >= 12;
+        PassHost ph = build_pass(P.comp, tom, masks, pc, n_loc, rb,
+                                 ((opt.cta_mode == 2 && can_big) || Lp >= 13) ? big_caps(Lp) : small_caps());
+        if (opt.cta_mode == 0 && can_big && !ph.caps.big && (ph.chunks.size() > 1 || ph.n_quad > 0))
+          ph = build_pass(P.comp, tom, masks, pc, n_loc, rb, big_caps(Lp));
+        P.passes.push_back(std::move(ph));
+      }
     }
     out.push_back(std::move(P));
   }

@@ -16,7 +16,7 @@ from ._lib import PsumError, check, lib
 
 INFO_KEYS = ('n_qubits', 'n_terms', 'n_xgroups', 'n_passes', 'n_remote_groups', 'is_hermitian',
              'is_diagonal', 'n_local_qubits', 'n_patterns', 'n_component_terms', 'tile_bits',
-             'n_global_parts', 'n_flat_groups', 'n_group_records', 'n_fast_groups', 'n_bundles')
+             'n_global_parts', 'n_flat_groups', 'n_group_records', 'n_fast_groups', 'n_bundles', 'n_quad_groups')
 
 
 def pack_masks(labels_or_masks):
@@ -121,8 +121,8 @@ class PauliSumEngine:
         check(lib().psum_set_option(self._h, key.encode(), int(value)))
 
     def info(self):
-        buf = (C.c_int64 * 16)()
-        check(lib().psum_info(self._h, buf, 16))
+        buf = (C.c_int64 * 17)()
+        check(lib().psum_info(self._h, buf, 17))
         return dict(zip(INFO_KEYS, [int(v) for v in buf]))
 
     def pass_info(self, p, g=0):

@@ -426,6 +426,36 @@ class WeightedPauliOperator(LegacyBaseOperator):
         psi = as_device_state(quantum_state, 1 << self.num_qubits)
         return self.engine.expect(psi), 0.0
 
+    def evaluate_with_result(self, result, statevector_mode, use_simulator_snapshot_mode=False,
+                             circuit_name_prefix=''):
+        """(mean, std_dev) from a backend result -- reference :757-812.  Statevector branch
+        (:793-802): ``result.get_statevector(prefix + 'psi')`` is psi and
+        ``result.get_statevector(prefix + label)`` is P|psi> for every non-identity Pauli; the mean is
+        sum_k w_k <psi|P_k psi> (identity terms add w_k).  The T overlaps are device reductions; the
+        states may be numpy arrays or CUDA tensors.  The snapshot branch (:784-792) reads the value
+        the simulator computed.  The shot-based branch (:803-811) is not part of the H.psi path."""
+        if self.is_empty():
+            raise AquaError('Operator is empty, check the operator.')
+        if use_simulator_snapshot_mode:
+            avg = result.data(circuit_name_prefix + 'snapshot_mode')['snapshots']['expectation_value']['expval'][0]['value']
+            if isinstance(avg, (list, tuple)):
+                avg = avg[0] + 1j * avg[1]
+            return avg, 0.0
+        if not statevector_mode:
+            raise AquaError('evaluate_with_result: only the statevector (and snapshot) branches are provided; '
+                            'the shot-based estimator is outside the Pauli-sum H.psi path')
+        from .engine import vec_dot
+        psi = as_device_state(result.get_statevector(circuit_name_prefix + 'psi'), 1 << self.num_qubits)
+        avg = 0.0
+        for weight, pauli in self._paulis:
+            if pauli.x_mask == 0 and pauli.z_mask == 0:
+                avg += weight
+            else:
+                psi_i = as_device_state(result.get_statevector(circuit_name_prefix + pauli.to_label()),
+                                        1 << self.num_qubits)
+                avg += weight * vec_dot(psi, psi_i)
+        return avg, 0.0
+
     def evolve(self, state_in, evo_time=0, num_time_slices=0, tol=1e-10):
         """exp(-i * evo_time * H) @ state_in -- the exact branch (num_time_slices == 0) of
         MatrixOperator.evolve (legacy/matrix_operator.py:319-355), by Krylov exponentiation on the
@@ -624,6 +654,12 @@ class ListOp(OperatorBase):
         self.oplist = list(oplist)
         self.coeff = coeff
 
+    distributive = True           # list_ops/list_op.py:108-118 (ComposedOp overrides it with False)
+
+    @staticmethod
+    def combo_fn(values):         # a plain ListOp keeps the list of results (list_op.py:60, lambda x: x)
+        return values
+
     def __len__(self):
         return len(self.oplist)
 
@@ -646,6 +682,10 @@ class ListOp(OperatorBase):
 
 class SummedOp(ListOp, _PauliSumMixin):
     """list_ops/summed_op.py: combo_fn = sum."""
+
+    @staticmethod
+    def combo_fn(values):
+        return sum(values)
 
     def __init__(self, oplist, coeff=1.0):
         ListOp.__init__(self, oplist, coeff)
@@ -682,10 +722,13 @@ class StateFnBase(OperatorBase):
 
 class VectorStateFn(StateFnBase):
     """state_fns/vector_state_fn.py: a state (or measurement) backed by a complex128 vector that
-    stays on the device."""
+    stays on the device.  As in the reference, ``adjoint()`` stores the CONJUGATED vector (and
+    conj(coeff)), and ``eval`` / ``to_matrix`` then use the stored vector as is (:76-79, :139-142,
+    :190-192: a plain, non-conjugating ``np.dot``)."""
 
-    def __init__(self, primitive, coeff=1.0, is_measurement=False):
+    def __init__(self, primitive, coeff=1.0, is_measurement=False, _conj=None):
         self._dev = as_device_state(primitive)
+        self._conj = _conj            # cached conj(primitive), shared with the adjoint
         self.coeff = coeff
         self.is_measurement = is_measurement
 
@@ -700,12 +743,17 @@ class VectorStateFn(StateFnBase):
     def device_vector(self):
         return self._dev
 
+    def _conj_vector(self):
+        if self._conj is None:
+            self._conj = self._dev.conj().resolve_conj()
+        return self._conj
+
     def to_matrix(self, massive=False):
         v = self._dev.cpu().numpy() * self.coeff
-        return np.conj(v) if self.is_measurement else v
+        return v.reshape(1, -1) if self.is_measurement else v
 
     def mul(self, scalar):
-        return VectorStateFn(self._dev, self.coeff * scalar, self.is_measurement)
+        return VectorStateFn(self._dev, self.coeff * scalar, self.is_measurement, _conj=self._conj)
 
     def add(self, other):
         if not isinstance(other, VectorStateFn):
@@ -715,23 +763,25 @@ class VectorStateFn(StateFnBase):
         return VectorStateFn(self._dev * self.coeff + other._dev * other.coeff, 1.0, self.is_measurement)
 
     def adjoint(self):
-        return VectorStateFn(self._dev, np.conj(self.coeff), not self.is_measurement)
+        return VectorStateFn(self._conj_vector(), np.conj(self.coeff), not self.is_measurement, _conj=self._dev)
 
     def compose(self, other):
         return ComposedOp([self, other])
 
     def eval(self, front=None):
-        """<self|front> for a measurement (vector_state_fn.py:165-196, rounded to 18 digits)."""
+        """sum_i self_i front_i for a measurement (vector_state_fn.py:165-196, rounded to 18 digits);
+        for ``~StateFn(v)`` the stored vector is conj(v), i.e. the value is <v|front>."""
         if front is None:
             return self
         if not self.is_measurement:
             raise ValueError('Cannot compute overlap with StateFn or Operator if not Measurement.')
-        if isinstance(front, ListOp):
-            return [self.eval(f) for f in front.oplist]
+        if isinstance(front, ListOp) and front.distributive:
+            return front.combo_fn([self.eval(f.mul(front.coeff)) for f in front.oplist])
         if not isinstance(front, VectorStateFn):
             front = StateFn(front)
         from .engine import vec_dot
-        val = vec_dot(self._dev, front.device_vector()) * self.coeff * front.coeff
+        # vec_dot conjugates its first argument: hand it conj(stored) to get the plain dot product
+        val = vec_dot(self._conj_vector(), front.device_vector()) * self.coeff * front.coeff
         return complex(np.round(val, decimals=EVAL_SIG_DIGITS))
 
 
@@ -762,12 +812,15 @@ class OperatorStateFn(StateFnBase):
             return self
         if not self.is_measurement:
             raise ValueError('Cannot compute overlap with StateFn or Operator if not Measurement.')
-        if isinstance(front, ListOp):
+        # ListOp carve-out of the reference (:199-203): only a plain ListOp (subclasses such as
+        # SummedOp / ComposedOp are excluded by its type() test), each element scaled by the list's
+        # coefficient BEFORE the evaluation -- so front.coeff enters as |front.coeff|^2
+        if type(front) is ListOp:  # pylint: disable=unidiomatic-typecheck
             vecs = [f if isinstance(f, VectorStateFn) else StateFn(f) for f in front.oplist]
             eng = self.primitive._engine_for()
             vals = eng.expect_batch([v.device_vector() for v in vecs])
-            return [complex(np.round(v * self.coeff * abs(s.coeff) ** 2 * front.coeff, EVAL_SIG_DIGITS))
-                    for v, s in zip(vals, vecs)]
+            return front.combo_fn([complex(np.round(v * self.coeff * abs(s.coeff * front.coeff) ** 2, EVAL_SIG_DIGITS))
+                                   for v, s in zip(vals, vecs)])
         if not isinstance(front, VectorStateFn):
             front = StateFn(front)
         val = self.primitive._engine_for().expect(front.device_vector())
@@ -776,6 +829,8 @@ class OperatorStateFn(StateFnBase):
 
 class ComposedOp(ListOp):
     """list_ops/composed_op.py:111-128: eval right-to-left."""
+
+    distributive = False
 
     def compose(self, other):
         return ComposedOp(self.oplist + [other], self.coeff)
@@ -795,7 +850,13 @@ class ComposedOp(ListOp):
 def StateFn(primitive, coeff=1.0, is_measurement=False):
     """Factory (state_fns/state_fn.py:47-92): vectors -> VectorStateFn, operators -> OperatorStateFn."""
     if isinstance(primitive, (VectorStateFn, OperatorStateFn)):
-        return primitive
+        # the reference wraps any OperatorBase in an OperatorStateFn; for an object that already is a
+        # state function this shim hands the same state back, with the requested coefficient and
+        # measurement flag applied instead of silently dropped
+        out = primitive
+        if bool(is_measurement) != bool(out.is_measurement):
+            out = out.adjoint()
+        return out.mul(coeff) if coeff != 1.0 else out
     if hasattr(primitive, 'to_vector_state_fn'):   # CircuitStateFn: prepare psi on the device
         return primitive.to_vector_state_fn()
     if isinstance(primitive, str):                 # basis state '0101' (state_fn.py:66-71)

@@ -244,6 +244,33 @@ def main():
         vals = R['MatrixExpectation']().convert(expr).eval()
         table.append([cplx(v) for v in vals])
     out['matrix_expectation_table'] = {'paulis': 'XYZI', 'states': states, 'values': table}
+    # coefficient semantics of the measurement chain: a ListOp front with a non-unit (complex) list
+    # coefficient (operator_state_fn.py:199-203 folds it into each element BEFORE the evaluation),
+    # element coefficients, a measurement coefficient, and VectorStateFn measurements with complex
+    # coefficients (vector_state_fn.py:76-79 adjoint stores the conjugated vector, :190-192 plain dot)
+    rng = np.random.default_rng(99)
+    coeff_cases = []
+    for lab, lcoef, mcoef in (('ZX', 2.0, 1.0), ('XY', 1 + 1j, 0.5), ('YZ', -0.5j, 2 - 1j)):
+        vs = [rng.standard_normal(4) + 1j * rng.standard_normal(4) for _ in range(3)]
+        ecs = [1.0, 0.5 - 0.25j, 2.0]
+        meas = (~R['StateFn'](R['PauliOp'](Pauli(lab)))) * mcoef
+        front = R['ListOp']([R['StateFn'](v) * ec for v, ec in zip(vs, ecs)], coeff=lcoef)
+        vals = R['MatrixExpectation']().convert(meas @ front).eval()
+        coeff_cases.append({'pauli': lab, 'list_coeff': cplx(lcoef), 'meas_coeff': cplx(mcoef),
+                            'elem_coeffs': [cplx(e) for e in ecs], 'states': [[cplx(a) for a in v] for v in vs],
+                            'values': [cplx(v) for v in vals]})
+    out['listop_coeff_cases'] = coeff_cases
+    vec_cases = []
+    for c_bra, c_ket in ((1.0, 1.0), (0.5 + 2j, 1.0), (1 - 1j, -0.25j)):
+        a = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+        b = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+        bra_adj = (R['StateFn'](a) * c_bra).adjoint()                 # ~(c a): stores conj(a), conj(c)
+        bra_direct = R['StateFn'](a, coeff=c_bra, is_measurement=True)   # stored vector used as is
+        ket = R['StateFn'](b) * c_ket
+        vec_cases.append({'a': [cplx(v) for v in a], 'b': [cplx(v) for v in b], 'c_bra': cplx(c_bra), 'c_ket': cplx(c_ket),
+                          'adjoint_eval': cplx(bra_adj.eval(ket)), 'direct_eval': cplx(bra_direct.eval(ket)),
+                          'adjoint_to_matrix': [cplx(v) for v in np.asarray(bra_adj.to_matrix()).reshape(-1)]})
+    out['vector_measurement_cases'] = vec_cases
     path = os.path.join(HERE, 'reference_run.json')
     with open(path, 'w') as f:
         json.dump(out, f)

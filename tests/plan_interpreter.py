@@ -19,9 +19,10 @@ GROUP_DT = np.dtype([('xt', '<u4'), ('meta', '<u4'), ('zt0', '<u4'), ('zt1', '<u
                      ('cf1', '<f8'), ('xl', '<u8'), ('ent', '<u2', (4,))])
 BUNDLE_DT = np.dtype([('xo', '<u4'), ('meta', '<u4'), ('xlo', '<u8')])
 CHUNK_DT = np.dtype([('g0', '<i4'), ('ng', '<i4'), ('p0', '<i4'), ('np', '<i4'), ('b0', '<i4'), ('nb', '<i4'),
-                     ('ns', '<u2'), ('pad0', '<u2'), ('pad1', '<u4'), ('s_cnt', 'u1', (32,))])
+                     ('ns', '<u2'), ('nq', '<u2'), ('q0', '<u4'), ('s_cnt', 'u1', (32,))])
 assert GROUP_DT.itemsize == 48 and CHUNK_DT.itemsize == 64 and BUNDLE_DT.itemsize == 16
 VAR_GENERAL = 63
+VAR_QUAD = 62
 
 
 def _ptr(a):
@@ -30,12 +31,13 @@ def _ptr(a):
 
 def export_pass(engine, g, p):
     """Arrays of pass p of global part g, or None when there is no such pass."""
-    counts = (C.c_int64 * 10)()
-    rc = lib().psum_plan_export(engine._h, g, p, counts, None, None, None, None, None, None, None, None, None, None)
+    counts = (C.c_int64 * 12)()
+    rc = lib().psum_plan_export(engine._h, g, p, counts, None, None, None, None, None, None, None, None, None, None, None)
     if rc != 0:
         return None
-    ng, npat, nterm, nch, L, nnf, has_im, hi_bit, nbun, rb = [int(v) for v in counts]
-    out = dict(L=L, n_nonfree=nnf, has_im=bool(has_im), hi_bit=hi_bit, rb=rb,
+    ng, npat, nterm, nch, L, nnf, has_im, hi_bit, nbun, rb, nquad, big = [int(v) for v in counts]
+    out = dict(L=L, n_nonfree=nnf, has_im=bool(has_im), hi_bit=hi_bit, rb=rb, big=bool(big),
+               quad_idx=np.zeros(nquad, np.uint16),
                groups=np.zeros(ng, GROUP_DT), bundles=np.zeros(nbun, BUNDLE_DT),
                pat_zt=np.zeros(npat, np.uint16), pat_inl=np.zeros(npat, np.uint16),
                pat_tptr=np.zeros(npat + 1, np.uint32), term_zb=np.zeros(nterm, np.uint64),
@@ -43,7 +45,7 @@ def export_pass(engine, g, p):
                fbit=np.zeros(16, np.uint8), nbit=np.zeros(64, np.uint8))
     rc = lib().psum_plan_export(engine._h, g, p, counts, _ptr(out['groups']), _ptr(out['pat_zt']), _ptr(out['pat_inl']),
                                 _ptr(out['pat_tptr']), _ptr(out['term_zb']), _ptr(out['term_val']), _ptr(out['chunks']),
-                                _ptr(out['fbit']), _ptr(out['nbit']), _ptr(out['bundles']))
+                                _ptr(out['fbit']), _ptr(out['nbit']), _ptr(out['bundles']), _ptr(out['quad_idx']))
     assert rc == 0
     return out
 
@@ -133,6 +135,11 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                     if not remote:
                         assert xt & ~int(regmask) == xo
                         assert np.array_equal(idx[(t ^ np.uint64(xt)).astype(np.int64)], idx ^ np.uint64(G['xl']))
+                if var == VAR_QUAD:
+                    contrib = quad_member(G, meta) * pv
+                    if herm and hbit:
+                        contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
+                    return contrib
                 # general evaluation from the class entry lists (every group carries them)
                 p, nent, flat = meta & 0xffff, (meta >> 16) & 7, (meta >> 21) & 1
                 D = np.zeros(1 << L, dtype=np.complex128)
@@ -168,6 +175,54 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                     contrib = np.where(((t >> np.uint64(hbit - 1)) & np.uint64(1)) == 0, contrib, 0.0)
                 return contrib
 
+            def quad_member(G, meta):
+                """D of a quadratic group through the separable tables the kernel rebuilds per tile,
+                checked against the direct sum over its patterns."""
+                nW = L - 5 - rb
+                raw = G.tobytes()
+                area = np.frombuffer(raw[8:32], dtype=np.uint8)
+                toff = int(np.frombuffer(raw[30:32], dtype='<u2')[0])
+                nseg = 2 + nW + 2 * rb + 1
+                pfirst = meta & 0xffff
+                npat_g = int(area[nseg])
+                zs = zt[pfirst:pfirst + npat_g].astype(np.uint64)
+                cs = cf[pfirst:pfirst + npat_g]
+                direct = np.zeros(1 << L)
+                for zz, cc in zip(zs, cs):
+                    direct += cc * _sign(t & zz)
+                if check:
+                    assert area[0] == 0 and all(area[i] <= area[i + 1] for i in range(nseg))
+                    assert toff % ((1 + nW + rb) * 32 + (1 + rb) * (1 << nW) + NA) == 0
+                    assert all(bin(int(zz)).count('1') <= 2 for zz in zs)
+
+                def seg_sum(seg, M, filt=None):
+                    v = 0.0
+                    for q in range(int(area[seg]), int(area[seg + 1])):
+                        if filt is not None and (int(zs[q]) >> 5) & (NA - 1) != filt:
+                            continue
+                        v += cs[q] * (1.0 - 2.0 * (bin(int(zs[q]) & M).count('1') & 1))
+                    return v
+                wsz = 1 << nW
+                lane_tabs = [[seg_sum(0 if tb == 0 else tb + 1, l) for l in range(32)] for tb in range(1 + nW + rb)]
+                w_tabs = [[seg_sum(1 if tb == 0 else 2 + nW + rb + tb - 1, w << (5 + rb)) for w in range(wsz)]
+                          for tb in range(1 + rb)]
+                ktab = [seg_sum(2 + nW + 2 * rb, 0, filt=m) for m in range(NA)]
+                lane_i = (t & np.uint64(31)).astype(np.int64)
+                w_i = (t >> np.uint64(5 + rb)).astype(np.int64)
+                r_i = reg.astype(np.int64)
+                LT, WT, KT = np.array(lane_tabs), np.array(w_tabs), np.array(ktab)
+                D = LT[0][lane_i] + WT[0][w_i]
+                for j in range(nW):
+                    D = D + LT[1 + j][lane_i] * (1.0 - 2.0 * ((w_i >> j) & 1))
+                for i in range(rb):
+                    D = D + (LT[1 + nW + i][lane_i] + WT[1 + i][w_i]) * (1.0 - 2.0 * ((r_i >> i) & 1))
+                for m in range(NA):
+                    if bin(m).count('1') == 2:
+                        D = D + KT[m] * (1.0 - 2.0 * (np.bitwise_count((r_i & m).astype(np.uint64)) & 1))
+                if check:
+                    assert np.allclose(D, direct, rtol=0, atol=1e-12 * (1.0 + np.abs(direct).max()))
+                return D.astype(np.complex128)
+
             def hbit_check(hbit, xo, remote):
                 if hbit:
                     assert not remote and xo and hbit - 1 >= 5 + rb and (xo >> (hbit - 1)) == 1
@@ -190,6 +245,10 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                     acc += member(G, g, xt & ~int(regmask), 0, meta >> 28, int(G['xl']) & ~regq)
                     g += 1
             assert g == ns
+            if check:       # the chunk's quadratic groups are listed in quad_idx[q0 : q0 + nq)
+                listed = [int(v) for v in ps['quad_idx'][int(ch['q0']):int(ch['q0']) + int(ch['nq'])]]
+                actual = [gi for gi in range(ng) if (int(grp[gi]['meta']) >> 22) & 63 == VAR_QUAD]
+                assert listed == actual
             seen = ns
             for B in bundles[int(ch['b0']):int(ch['b0']) + int(ch['nb'])]:
                 xo, remote = int(B['xo']) & 0x7fffffff, int(B['xo']) >> 31

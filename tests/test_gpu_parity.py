@@ -52,16 +52,19 @@ def test_two_local_tiled(tile_bits, low_bits, reg_bits):
     assert info['n_bundles'] < info['n_group_records']        # partner loads are shared
 
 
+@pytest.mark.parametrize('cta_mode', [0, 1, 2])
 @pytest.mark.parametrize('reg_bits', [3, 4])
 @pytest.mark.parametrize('kind', ['c4', 'c5', 'molecular'])
-def test_benchmark_families_both_register_widths(kind, reg_bits):
+def test_benchmark_families_both_register_widths(kind, reg_bits, cta_mode):
     if kind == 'c4':
         n, x, z, y, c = W.ising_heisenberg(18, n_triples=3000, seed=30)
     elif kind == 'c5':
         n, x, z, y, c = W.random_weighted_paulis(18, 3000, 4, seed=34)
     else:
         n, x, z, y, c = W.molecular_style(14)
-    eng = _check(n, x, z, y, c, {'reg_bits': reg_bits})
+    eng = _check(n, x, z, y, c, {'reg_bits': reg_bits, 'cta_mode': cta_mode})
+    if kind == 'c4':
+        assert eng.info()['n_quad_groups'] >= n          # separable-table path is exercised
     psi = _state(n, 5)
     ref = np.vdot(psi, co.apply(n, x, z, y, c, psi))
     assert abs(eng.expect_host(psi) - ref) <= RTOL * max(1.0, abs(ref))

@@ -11,7 +11,7 @@ torch = pytest.importorskip('torch')
 pytestmark = pytest.mark.gpu
 
 from oracle import pauli_oracle as po        # noqa: E402
-from qiskit_aqua_b200 import (I, ListOp, MatrixExpectation, NumPyEigensolver, NumPyMinimumEigensolver,  # noqa: E402
+from qiskit_aqua_b200 import (AquaError, I, ListOp, MatrixExpectation, NumPyEigensolver, NumPyMinimumEigensolver,  # noqa: E402
                               Pauli, StateFn, WeightedPauliOperator, X, Y, Z, max_cut, random_graph,
                               sample_most_likely)
 
@@ -25,6 +25,46 @@ AUX2 = {'paulis': [{'coeff': {'imag': 0.0, 'real': 0.5}, 'label': 'II'},
                    {'coeff': {'imag': 0.0, 'real': 0.5}, 'label': 'ZZ'},
                    {'coeff': {'imag': 0.0, 'real': 0.5}, 'label': 'YY'},
                    {'coeff': {'imag': 0.0, 'real': -0.5}, 'label': 'XX'}]}
+
+
+class _StatevectorResult:
+    """Stand-in for a backend Result holding the statevectors of construct_evaluation_circuit
+    (statevector mode): 'psi' and one circuit per non-identity Pauli, named by its label."""
+
+    def __init__(self, psi, terms, prefix=''):
+        self._sv = {prefix + 'psi': psi}
+        for _, lab in terms:
+            if set(lab) != {'I'}:
+                self._sv[prefix + lab] = po.pauli_csr(lab).dot(psi)
+
+    def get_statevector(self, name):
+        return self._sv[name]
+
+    def data(self, name):
+        return {'snapshots': {'expectation_value': {'expval': [{'value': [0.25, -0.5]}]}}}
+
+
+def test_evaluate_with_result_statevector_mode():
+    # mirrors test_weighted_pauli_operator.py:483-496 (test_evaluate_statevector_mode): the value from
+    # the per-Pauli statevectors equals evaluate_with_statevector to 10 places
+    rng = np.random.default_rng(3)
+    paulis = [Pauli(''.join(lab)) for lab in itertools.product('IXYZ', repeat=3)]
+    weights = rng.random(len(paulis)) + 1j * rng.random(len(paulis))
+    op = WeightedPauliOperator.from_list(paulis, weights)
+    psi = rng.standard_normal(8) + 1j * rng.standard_normal(8)
+    psi /= np.linalg.norm(psi)
+    terms = [(w, p.to_label()) for w, p in op.paulis]
+    reference = op.evaluate_with_statevector(psi)
+    for prefix in ('', 'pre_'):
+        actual = op.evaluate_with_result(_StatevectorResult(psi, terms, prefix), statevector_mode=True,
+                                         circuit_name_prefix=prefix)
+        assert abs(reference[0] - actual[0]) < 1e-10 and actual[1] == 0.0
+    snap = op.evaluate_with_result(_StatevectorResult(psi, terms), statevector_mode=True, use_simulator_snapshot_mode=True)
+    assert snap[0] == 0.25 - 0.5j
+    with pytest.raises(AquaError):
+        op.evaluate_with_result(_StatevectorResult(psi, terms), statevector_mode=False)
+    with pytest.raises(AquaError):
+        WeightedPauliOperator(paulis=[]).evaluate_with_result(None, True)
 
 
 def test_evaluate_with_statevector_g13():

@@ -74,7 +74,8 @@ def test_exported_plan_reproduces_oracle(n, T, opts, kw):
     passes = pi.export_part(eng, 0)
     assert len(passes) == info['n_passes'] > 0
     assert sum(len(ps['groups']) for ps in passes) == info['n_group_records']
-    assert sum(len(ps['bundles']) for ps in passes) == info['n_bundles'] <= info['n_group_records']
+    singles = sum(int(ch['ns']) for ps in passes for ch in ps['chunks'])
+    assert sum(len(ps['bundles']) for ps in passes) + singles == info['n_bundles'] <= info['n_group_records']
     assert all(ps['rb'] == opts.get('reg_bits', 3) for ps in passes)
     assert sum(len(ps['pat_zt']) for ps in passes) == info['n_patterns']
     assert sum(len(ps['term_val']) for ps in passes) == info['n_component_terms']     # every term exactly once
@@ -148,6 +149,29 @@ def test_sharded_parts_reproduce_oracle(world, rb):
                 pi.run_part(passes, shards[rank ^ g], y)
         assert np.linalg.norm(y - want.reshape(world, -1)[rank]) <= 1e-12 * np.linalg.norm(want)
     assert len(seen_parts) > 1
+
+
+def test_quadratic_groups_are_planned_and_evaluated():
+    """Ising/Heisenberg + Z X Z decorations: the heavy groups (many <= 2-local z-patterns) take the
+    separable-table path (variant 62); the interpreter rebuilds the tables and checks them against
+    the direct pattern sum."""
+    from qiskit_aqua_b200 import workloads as W
+    for rb, L in ((3, 11), (4, 11), (3, 12), (4, 13)):
+        n = 14
+        _, x, z, ypow, c = W.ising_heisenberg(n, n_triples=900, seed=5)
+        eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': L, 'reg_bits': rb})
+        passes = pi.export_part(eng, 0)
+        nq = sum(int(np.count_nonzero(((ps['groups']['meta'] >> 22) & 63) == pi.VAR_QUAD)) for ps in passes)
+        assert nq >= n                                  # every single-X group + the diagonal one
+        assert sum(int(ch['nq']) for ps in passes for ch in ps['chunks']) == nq
+        rng = np.random.default_rng(rb * 100 + L)
+        psi = random_state(n, rng)
+        y = np.zeros(1 << n, dtype=np.complex128)
+        e = pi.run_part(passes, psi, y)
+        want = po.mf_apply(n, x, z, ypow, np.asarray(c, dtype=np.complex128), psi)
+        assert np.linalg.norm(y - want) <= 1e-12 * np.linalg.norm(want)
+        eh = pi.run_part(passes, psi, None, herm=True)
+        assert abs(eh.real - np.vdot(psi, want).real) <= 1e-11 * max(1.0, abs(np.vdot(psi, want)))
 
 
 @pytest.mark.parametrize('rb', [3, 4])

@@ -189,3 +189,29 @@ def test_product_matrix_expectation_vs_reference_run():
         meas = ~StateFn(PauliOp(Pauli(lab)))
         vals = MatrixExpectation().convert(meas @ ListOp([StateFn(np.array(v, dtype=complex)) for v in tab['states']])).eval()
         np.testing.assert_allclose(vals, [_c(w) for w in row], atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_listop_and_measurement_coefficients_vs_reference_run():
+    """Coefficient semantics of the opflow measurement chain, recorded by running the reference:
+    a ListOp front's coefficient enters as |coeff|^2 (operator_state_fn.py:199-203), adjoint()
+    conjugates vector AND coefficient, a directly constructed measurement uses its vector as is
+    (vector_state_fn.py:76-79, :139-142, :190-192)."""
+    pytest.importorskip('torch')
+    from qiskit_aqua_b200 import ListOp, MatrixExpectation, PauliOp, StateFn
+    for case in REF['listop_coeff_cases']:
+        meas = (~StateFn(PauliOp(Pauli(case['pauli'])))) * _c(case['meas_coeff'])
+        front = ListOp([StateFn(np.array([_c(a) for a in v])) * _c(ec)
+                        for v, ec in zip(case['states'], case['elem_coeffs'])], coeff=_c(case['list_coeff']))
+        vals = MatrixExpectation().convert(meas @ front).eval()
+        np.testing.assert_allclose(vals, [_c(v) for v in case['values']], atol=1e-12)
+    for case in REF['vector_measurement_cases']:
+        a = np.array([_c(v) for v in case['a']])
+        b = np.array([_c(v) for v in case['b']])
+        ket = StateFn(b) * _c(case['c_ket'])
+        bra_adj = (StateFn(a) * _c(case['c_bra'])).adjoint()
+        bra_direct = StateFn(a, coeff=_c(case['c_bra']), is_measurement=True)
+        assert abs(bra_adj.eval(ket) - _c(case['adjoint_eval'])) < 1e-12
+        assert abs(bra_direct.eval(ket) - _c(case['direct_eval'])) < 1e-12
+        np.testing.assert_allclose(np.asarray(bra_adj.to_matrix()).reshape(-1),
+                                   [_c(v) for v in case['adjoint_to_matrix']], atol=1e-14)
