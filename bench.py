@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument('--low-bits', type=int, default=0)
     ap.add_argument('--reg-bits', type=int, default=0)
     ap.add_argument('--cta-mode', type=int, default=-1)
+    ap.add_argument('--min-bundle', type=int, default=0)
+    ap.add_argument('--share-weight', type=int, default=-1)
     return ap.parse_args()
 
 
@@ -275,6 +277,10 @@ def main():
         opts['reg_bits'] = args.reg_bits
     if args.cta_mode >= 0:
         opts['cta_mode'] = args.cta_mode
+    if args.min_bundle:
+        opts['min_bundle'] = args.min_bundle
+    if args.share_weight >= 0:
+        opts['share_weight'] = args.share_weight
     eng = PauliSumEngine(n_total, x, z, y, c, opts)
     recv = None
     if world > 1:
@@ -437,6 +443,29 @@ def main():
         parity['product_state_oracle'] = 'oracle/pauli_oracle.py product_state_expect (closed form, O(T n))'
         parity['ok'] = bool(parity['max_rel_err_y'] <= 1e-10 and parity['rel_err_energy_product_state'] <= 1e-10 and
                             parity['rel_err_energy_fused_vs_dot'] <= 1e-10)
+
+    # ---- sharded Lanczos == single-GPU Lanczos (the on-device eigensolver on the sharded matvec) ----
+    if parity is not None and world > 1:
+        from qiskit_aqua_b200 import workloads as W
+        nl, xl_, zl_, yl_, cl_ = W.two_local_random(22, 700, seed=22)
+        engl = PauliSumEngine(nl, xl_, zl_, yl_, cl_)
+        uid2 = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        engl.shard(rank, world, uid2[0])
+        rs = engl.lanczos(k=2, tol=1e-12, want_residuals=True)
+        single = [0.0, 0.0]
+        if rank == 0:
+            single = PauliSumEngine(nl, xl_, zl_, yl_, cl_).lanczos(k=2, tol=1e-12)['evals'].tolist()
+        t = torch.tensor(single, dtype=torch.float64, device='cuda')
+        dist.broadcast(t, src=0)
+        single = t.cpu().numpy()
+        parity['sharded_lanczos'] = {'qubits': nl, 'terms': len(xl_), 'k': 2, 'tol': 1e-12, 'matvecs': rs['iters'],
+                                     'evals': rs['evals'].tolist(),
+                                     'max_abs_err_vs_single_gpu': float(np.abs(rs['evals'] - single).max()),
+                                     'max_residual': float(rs['resid'].max())}
+        parity['ok'] = bool(parity['ok'] and parity['sharded_lanczos']['max_abs_err_vs_single_gpu'] <= 1e-9 and
+                            parity['sharded_lanczos']['max_residual'] <= 1e-6)
+        del engl
 
     # ---- NVLink: exchange time on the communication stream, and how much of it is hidden ----------
     nvlink = None

@@ -118,6 +118,22 @@ int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* psi_dev, do
 int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev, double* out,
                       psum_stream_t stream);
 
+/* Dense 2^n x 2^n matrix of the sum, row-major complex128 on the device (n <= 14): what the reference
+ * obtains from to_matrix() (list_ops/list_op.py:306-329, primitive_ops/pauli_op.py:151-153) and feeds
+ * to np.linalg.eig when k >= 2^n - 1 (numpy_eigen_solver.py:171-173).  Not on the hot path. */
+int psum_to_dense(psum_handle_t h, void* mat_dev, psum_stream_t stream);
+
+/* Inverse transform of psum_to_dense ("next" row 4 of SURVEY 8f): Pauli weights of a dense matrix,
+ * replacing the 4^n sparse products tr(P M)/2^n of op_converter.to_weighted_pauli_operator
+ * (legacy/op_converter.py:35-100) by one Walsh-Hadamard transform per x-mask on the device.
+ * w_dev[x * 2^n + z] = weight(x, z) * (-i)^{popc(x & z)}; n_qubits <= 12. */
+int psum_pauli_decompose(const void* mat_dev, int n_qubits, void* w_dev, psum_stream_t stream);
+/* <psi|H_j|psi> of n_ops operators against one device state (aux operators
+ * numpy_eigen_solver.py:208-226, qEOM commutators q_equation_of_motion.py:400-416): all passes are
+ * queued back to back, one host synchronisation for the n_ops results (out = 2 * n_ops doubles). */
+int psum_expect_multi(const psum_handle_t* hs, int n_ops, const void* psi_dev, double* out,
+                      psum_stream_t stream);
+
 /* ---- diagonal (all-Z) operators: numpy_eigen_solver.py:163-169 ------------------------ */
 /* d_dev[i] = Re sum_k c_k (-1)^popc(i & z_k) as float64[N] on the device. */
 int psum_diag(psum_handle_t h, double* d_dev, psum_stream_t stream);

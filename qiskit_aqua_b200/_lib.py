@@ -31,6 +31,9 @@ SIGNATURES = {
     'psum_expect_host': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),
     'psum_bra_apply': (C.c_int, [_vp, _vp, _vp, _dp, _vp]),
     'psum_expect_batch': (C.c_int, [_vp, C.c_int, _vp, _dp, _vp]),
+    'psum_to_dense': (C.c_int, [_vp, _vp, _vp]),
+    'psum_pauli_decompose': (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    'psum_expect_multi': (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _dp, _vp]),
     'psum_diag': (C.c_int, [_vp, _vp, _vp]),
     'psum_diag_kmin': (C.c_int, [_vp, C.c_int, _dp, _u64p, _vp]),
     'psum_lanczos': (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int64, _dp, _vp,

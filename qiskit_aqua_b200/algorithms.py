@@ -113,43 +113,96 @@ class NumPyEigensolver:
             self._k = min(self._in_k, 2 ** self._operator.num_qubits)
 
     # -- solve --------------------------------------------------------------------------------------
+    # dense branch (k >= 2^n - 1, or more pairs than the Lanczos basis holds, or a non-Hermitian sum):
+    # the matrix is written on the device and diagonalised there by the dense library routine, as the
+    # reference does with np.linalg.eig (:171-173).  Bounded by the size of the dense matrix.
+    DENSE_MAX_QUBITS = 13
+    LANCZOS_MAX_K = 120
+
+    def _solve_dense(self, eng, n, k_keep):
+        if n > self.DENSE_MAX_QUBITS:
+            raise AquaError('NumPyEigensolver: %d eigenpairs of a %d-qubit operator need the dense branch, which is '
+                            'limited to %d qubits on the device (the reference would build a %d x %d matrix)'
+                            % (k_keep, n, self.DENSE_MAX_QUBITS, 1 << n, 1 << n))
+        mat = eng.to_dense()
+        if eng.info()['is_hermitian']:
+            w, v = torch.linalg.eigh(mat)
+            w = w.to(torch.complex128)
+        else:
+            w, v = torch.linalg.eig(mat)
+        wn = w.cpu().numpy()
+        order = np.argsort(wn)[:k_keep] if k_keep > 1 else np.array([int(np.argmin(wn.real))])   # :177-180
+        sel = torch.from_numpy(order.astype(np.int64)).cuda()
+        self._ret['eigvals'] = wn[order]
+        self._ret['eigvecs'] = v[:, sel].t().contiguous()
+
     def _solve(self):
         eng = self._operator._engine_for()
         info = eng.info()
         n = info['n_qubits']
         N = 1 << n
         if info['is_diagonal']:
-            vals, idx = eng.diag_kmin(self._k)                       # :163-169
+            if self._k * N * 16 > 8 * 2 ** 30:
+                raise AquaError('NumPyEigensolver: %d one-hot eigenvectors of a %d-qubit diagonal operator do not fit '
+                                '(the reference allocates the same 2^n x k array)' % (self._k, n))
+            if info['is_hermitian'] and self._k <= 32:
+                vals, idx = eng.diag_kmin(self._k)                   # :163-169, k fused min-sweeps
+                idx_t = torch.from_numpy(idx.astype(np.int64)).cuda()
+                vals = vals.astype(np.float64)
+            else:
+                # many values (filter_criterion asks for all 2^n), or complex weights: one device sort.
+                # np.sort / np.argsort order: ascending value (complex: real, then imaginary part),
+                # ties by lower index -> stable sorts
+                if info['is_hermitian']:
+                    d = eng.diag()
+                    _, order = torch.sort(d, stable=True)
+                    vals = d[order[:self._k]].cpu().numpy()
+                else:
+                    ones = torch.ones(N, dtype=torch.complex128, device='cuda')
+                    d = eng.apply(ones)                              # diagonal operator: (H 1)[i] = H[i, i]
+                    _, o1 = torch.sort(d.imag, stable=True)
+                    _, o2 = torch.sort(d.real[o1], stable=True)
+                    order = o1[o2]
+                    vals = d[order[:self._k]].cpu().numpy()
+                idx_t = order[:self._k]
             vecs = torch.zeros((self._k, N), dtype=torch.complex128, device='cuda')
-            vecs[torch.arange(self._k, device='cuda'), torch.from_numpy(idx.astype(np.int64)).cuda()] = 1.0
-            self._ret['eigvals'] = vals.astype(np.float64)
+            vecs[torch.arange(self._k, device='cuda'), idx_t] = 1.0
+            self._ret['eigvals'] = vals
             self._ret['eigvecs'] = vecs
             return
         # reference quirk (:171-173): for k >= 2^n - 1 the dense np.linalg.eig branch returns ALL 2^n
         # eigenpairs (not truncated to k); aux operators are still evaluated for the first k only
-        k_eff = N if self._k >= N - 1 else self._k
-        try:
-            r = eng.lanczos(k=k_eff, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
-        except PsumError as ex:
-            if ex.code == ERR_NOT_HERMITIAN:
-                raise AquaError('NumPyEigensolver on the GPU needs a Hermitian Pauli sum '
-                                '(real coefficients); no CPU fallback is provided') from ex
-            raise
+        if self._k >= N - 1:
+            return self._solve_dense(eng, n, N)
+        if not info['is_hermitian'] or self._k > self.LANCZOS_MAX_K:
+            # eigs(which='SR') accepts complex weights (Arnoldi); on the device only the dense routine does
+            if n > self.DENSE_MAX_QUBITS:
+                why = 'a non-Hermitian Pauli sum (complex label coefficients)' if not info['is_hermitian'] \
+                    else 'k = %d > %d' % (self._k, self.LANCZOS_MAX_K)
+                raise AquaError('NumPyEigensolver on the GPU: %s needs the dense branch, limited to %d qubits; '
+                                'no CPU fallback is provided' % (why, self.DENSE_MAX_QUBITS))
+            return self._solve_dense(eng, n, self._k)
+        r = eng.lanczos(k=self._k, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
         self._ret['eigvals'] = r['evals'].astype(np.complex128)      # eigs returns complex values
         self._ret['eigvecs'] = r['evecs']
 
     def _eval_aux_operators(self, wavefn, threshold=1e-12):
-        values = []
-        for operator in self._aux_operators:
+        """:208-226 -- every aux operator against the eigenvector that is already on the device; all
+        their passes are queued back to back and read with one synchronisation (psum_expect_multi)."""
+        from .engine import expect_multi
+        values = [None] * len(self._aux_operators)
+        live = []
+        for j, operator in enumerate(self._aux_operators):
             if operator is None:
-                values.append(None)
                 continue
-            value = 0.0
+            values[j] = (0.0, 0)
             terms = _terms_of(operator) if isinstance(operator, (_PauliSumMixin, WeightedPauliOperator)) else None
             if terms and any(w != 0 for w, _ in terms):
-                value = operator._engine_for().expect(wavefn)
-                value = value.real if abs(value.real) > threshold else 0.0
-            values.append((value, 0))
+                live.append((j, operator._engine_for()))
+        if live:
+            res = expect_multi([e for _, e in live], wavefn)
+            for (j, _), value in zip(live, res):
+                values[j] = (value.real if abs(value.real) > threshold else 0.0, 0)
         return np.array(values, dtype=object)
 
     def _get_energies(self):

@@ -391,6 +391,12 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "reg_bits") {
     if (value != 3 && value != 4) return fail(PSUM_ERR_INVALID, "reg_bits must be 3 or 4");
     h->opt.reg_bits = (int)value;
+  } else if (k == "share_weight") {
+    if (value < 0 || value > 10000) return fail(PSUM_ERR_INVALID, "share_weight must be 0..10000 (percent)");
+    h->opt.share_weight = (int)value;
+  } else if (k == "min_bundle") {
+    if (value < 2 || value > 255) return fail(PSUM_ERR_INVALID, "min_bundle must be 2..255");
+    h->opt.min_bundle = (int)value;
   } else if (k == "cta_mode") {
     if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "cta_mode must be 0 (auto), 1 (two CTAs per SM) or 2 (one big CTA)");
     h->opt.cta_mode = (int)value;
@@ -827,6 +833,9 @@ extern "C" int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev
 extern "C" int psum_diag(psum_handle_t h, double* d_dev, psum_stream_t stream) {
   if (!h || !d_dev) return fail(PSUM_ERR_INVALID, "null argument");
   if (!h->diagonal) return fail(PSUM_ERR_NOT_DIAGONAL, "operator has X/Y terms");
+  if (!h->hermitian)
+    return fail(PSUM_ERR_NOT_HERMITIAN, "psum_diag returns a real diagonal: the operator has complex weights "
+                "(apply it to the all-ones vector for the complex diagonal)");
   if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
   PS_TRY(upload(h));
   const DevPart* D0 = nullptr;
@@ -860,6 +869,52 @@ extern "C" int psum_to_dense(psum_handle_t h, void* mat_dev, psum_stream_t strea
   }
   CUDA_TRY(cudaGetLastError());
   return PSUM_OK;
+}
+
+// Inverse transform: dense matrix -> Pauli weights (legacy/op_converter.py:35-100 computes
+// tr(P M) / 2^n with 4^n sparse products).  mat_dev and w_dev are 2^n x 2^n complex128 row-major on the
+// device; w_dev[x][z] = weight of the label Pauli with masks (x, z) times (-i)^{popc(x & z)}.
+extern "C" int psum_pauli_decompose(const void* mat_dev, int n_qubits, void* w_dev, psum_stream_t stream) {
+  if (!mat_dev || !w_dev) return fail(PSUM_ERR_INVALID, "null argument");
+  if (n_qubits < 1 || n_qubits > 12) return fail(PSUM_ERR_INVALID, "pauli_decompose: n_qubits must be 1..12");
+  const size_t smem = sizeof(double2) << n_qubits;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_pauli_decompose, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)std::min<uint64_t>(1ull << n_qubits, (uint64_t)sms * 2);
+  k_pauli_decompose<<<grid, kThreads, smem, (cudaStream_t)stream>>>((const double2*)mat_dev, (double2*)w_dev, n_qubits);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
+// <psi|H_j|psi> for several operators (aux operators: numpy_eigen_solver.py:208-226; qEOM commutator
+// lists) against ONE state: the operators' passes run back to back on the stream and the host reads
+// the n_ops scalars with a single synchronisation.  out = 2 * n_ops doubles.
+extern "C" int psum_expect_multi(const psum_handle_t* hs, int n_ops, const void* psi_dev, double* out,
+                                 psum_stream_t stream) {
+  if (!hs || !out || n_ops < 1 || n_ops > 256 || !psi_dev) return fail(PSUM_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double2* psi = (const double2*)psi_dev;
+  psum_handle_s* first = nullptr;
+  for (int j = 0; j < n_ops; ++j) {
+    psum_handle_s* h = hs[j];
+    if (!h) return fail(PSUM_ERR_INVALID, "null handle %d", j);
+    if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle %d is sharded", j);
+    if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+    if (first && h->n != first->n) return fail(PSUM_ERR_INVALID, "operators act on different numbers of qubits");
+    PS_TRY(upload(h));
+    if (!first) first = h;
+    size_t pcount = 0;
+    for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st));
+    k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, first->d_scalar + j, 0);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return fetch_scalars(first, n_ops, out, st);
 }
 
 extern "C" int psum_diag_kmin(psum_handle_t h, int k, double* vals, uint64_t* idx, psum_stream_t stream) {

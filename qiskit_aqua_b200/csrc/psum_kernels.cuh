@@ -593,6 +593,34 @@ k_to_dense(double2* __restrict__ H, const SimpleGroup* __restrict__ groups, int 
   }
 }
 
+// Pauli decomposition of a dense matrix (inverse of k_to_dense): for every x-mask the generalised
+// diagonal d_x[i] = M[i][i ^ x] is Walsh-Hadamard transformed over i,
+//   W[x][z] = 2^-n sum_i (-1)^{popc(i & z)} M[i][i ^ x]      ( = weight(x, z) * (-i)^{popc(x & z)} ).
+// One CTA per x; the row lives in shared memory (n <= 12: 64 KB).
+__global__ void __launch_bounds__(kThreads)
+k_pauli_decompose(const double2* __restrict__ M, double2* __restrict__ Wout, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* row = reinterpret_cast<double2*>(smem_raw);
+  const uint64_t N = 1ull << n;
+  for (uint64_t x = blockIdx.x; x < N; x += gridDim.x) {
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < N; i += blockDim.x) row[i] = M[i * N + (i ^ x)];
+    __syncthreads();
+    for (uint64_t h = 1; h < N; h <<= 1) {
+      for (uint64_t p = threadIdx.x; p < N / 2; p += blockDim.x) {
+        const uint64_t lo = ((p & ~(h - 1)) << 1) | (p & (h - 1)), hi = lo | h;
+        const double2 a = row[lo], b = row[hi];
+        row[lo] = make_double2(a.x + b.x, a.y + b.y);
+        row[hi] = make_double2(a.x - b.x, a.y - b.y);
+      }
+      __syncthreads();
+    }
+    const double inv = 1.0 / (double)N;
+    for (uint64_t z = threadIdx.x; z < N; z += blockDim.x)
+      Wout[x * N + z] = make_double2(row[z].x * inv, row[z].y * inv);
+  }
+}
+
 // sum `count` complex partials in a fixed order -> out[0]  (single block)
 __global__ void __launch_bounds__(kThreads)
 k_reduce_partials(const double2* __restrict__ partial, int count, double2* __restrict__ out,

@@ -200,6 +200,9 @@ struct PlanOptions {
   int plan_tries = 8;  // randomised greedy restarts of the pass planner; the cheapest plan wins
   int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)
   int reg_bits = 3;    // 3: 8 amplitudes per thread, 256-thread CTAs; 4: 16 per thread, 128-thread CTAs
+  int share_weight = 100;  // percent: weight of the partner-load term when the register qubits are chosen
+  int min_bundle = 2;  // a bundle of fewer members, all of them fast, is split into singles (own loads,
+                       // straight-line loops): sharing only pays when enough members use one load set
   int cta_mode = 0;    // 0 auto (a pass that needs several chunks or holds quadratic groups runs as one
                        // big CTA per SM), 1 always two CTAs per SM, 2 always one big CTA
   int kernel = 0;  // 0 auto, 1 streaming only, 2 tiled
@@ -347,7 +350,8 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
 inline PassHost build_pass(const std::vector<CompTerm>& comp,
                            const std::vector<std::vector<int>>& terms_of_mask,
                            const std::vector<uint64_t>& masks, const PassChoice& pc, int n_loc, int rb,
-                           const ChunkCaps caps = ChunkCaps()) {
+                           const ChunkCaps caps = ChunkCaps(), int min_bundle = 2, int share_weight = 100) {
+  const double share_w = 0.01 * share_weight;
   PassHost P;
   P.caps = caps;
   P.free_mask = pc.free_mask;
@@ -388,19 +392,50 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
         uint64_t rm = 0;
         for (int i : pick) rm |= 1ull << cand[i];
         keys.clear();
-        double ccost = 0.0;
+        // cost of the pass in SM cycles per warp and round under this choice of register qubits
+        // (shared-memory pipe: 1 wavefront / cycle; issue: 4 instructions / cycle):
+        //   partner load set      4 NA wavefronts
+        //   fast group            ~12   (two inline slots; slot-1 class must be 0 or the x-mask's register part)
+        //   quadratic group       ~30   (separable tables; independent of the classes)
+        //   general group         ~8 + 9 per class entry + 3 per pattern
+        double gcost = 0.0;
         for (size_t m = 0; m < pc.members.size(); ++m) {
           const uint64_t xl = masks[pc.members[m]];
           keys.push_back(xl & ~rm);   // local and remote groups alike: equal outside the register qubits
+          const std::vector<uint64_t>& zs = zsets[m];
+          bool all_real = true, le2 = true;
+          for (uint64_t zk : zs) {
+            if (zk & 1ull) all_real = false;
+            if (popc64(zk >> 1) > 2) le2 = false;
+          }
+          if (all_real && le2 && (int)zs.size() >= kQuadMinPatterns) {
+            gcost += 30.0;
+            continue;
+          }
           cls.clear();
-          for (uint64_t zk : zsets[m]) cls.push_back(((zk >> 1) & rm) << 1 | (zk & 1ull));
-          std::sort(cls.begin(), cls.end());
-          ccost += (double)(std::unique(cls.begin(), cls.end()) - cls.begin()) - 1.0;
+          for (uint64_t zk : zs) cls.push_back(((zk >> 1) & rm) << 1 | (zk & 1ull));
+          bool fast = false;
+          if (zs.size() <= 2) {
+            // slot 0 must be a real class-0 pattern (or absent); slot 1: class 0 or the register part of x
+            const uint64_t xr = xl & rm;
+            int n_r0 = 0, n_ok1 = 0;
+            for (uint64_t ck : cls) {
+              if (ck == 0) ++n_r0;
+              else if ((ck >> 1) == 0 || (ck >> 1) == xr) ++n_ok1;
+            }
+            fast = (zs.size() == 1) ? (n_r0 + n_ok1 == 1) : (n_r0 >= 1 && n_r0 + n_ok1 == 2);
+          }
+          if (fast) {
+            gcost += 12.0;
+          } else {
+            std::sort(cls.begin(), cls.end());
+            const double ncls = (double)(std::unique(cls.begin(), cls.end()) - cls.begin());
+            gcost += 8.0 + 9.0 * ncls + 3.0 * (double)zs.size();
+          }
         }
         std::sort(keys.begin(), keys.end());
         const double nb = (double)(std::unique(keys.begin(), keys.end()) - keys.begin());
-        // wavefronts: a bundle = NA LDS.128 of 4 wavefronts per warp; an extra class ~ NA DADD + a branch
-        const double cost = 4.0 * NA * nb + 0.5 * NA * ccost;
+        const double cost = share_w * 4.0 * NA * nb + gcost;
         if (best_cost < 0.0 || cost < best_cost) {
           best_cost = cost;
           best = pick;
@@ -635,13 +670,23 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     cr.q0 = (uint32_t)P.quad_idx.size();
     auto s_index = [&](const SubGroup& sg) { return (int)((sg.G.meta >> 19) & 1u) * NA + (sg.var & (NA - 1)); };
     std::vector<size_t> singles, multi;
+    // a run whose members are all local fast groups and that is shorter than min_bundle is emitted as
+    // singles (each member loads its own partners); runs are then referenced by (run, member) pairs
+    struct Single { size_t r, q; };
+    std::vector<Single> single_members;
     for (size_t r = r0; r < r1; ++r) {
-      const SubGroup& sg = subs[runs[r].s0];
-      if (runs[r].s1 - runs[r].s0 == 1 && !sg.remote && sg.var != kVarGeneral) singles.push_back(r);
-      else multi.push_back(r);
+      bool all_fast = !subs[runs[r].s0].remote;
+      for (size_t q = runs[r].s0; q < runs[r].s1; ++q)
+        if (subs[q].var >= 2 * NA) all_fast = false;
+      if (all_fast && (int)(runs[r].s1 - runs[r].s0) < std::max(2, min_bundle)) {
+        for (size_t q = runs[r].s0; q < runs[r].s1; ++q) single_members.push_back({r, q});
+      } else {
+        multi.push_back(r);
+      }
     }
+    for (const Single& sm : single_members) singles.push_back(sm.q);
     std::stable_sort(singles.begin(), singles.end(), [&](size_t a, size_t b) {
-      return s_index(subs[runs[a].s0]) < s_index(subs[runs[b].s0]);
+      return s_index(subs[a]) < s_index(subs[b]);
     });
     int pl = 0, gl = 0;
     int nq_emitted = 0;
@@ -675,8 +720,8 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
       const int msb = 31 - __builtin_clz(xo);
       return msb >= kRegBitLo + rb ? (uint32_t)(msb + 1) : 0u;
     };
-    for (size_t r : singles) {
-      SubGroup& sg = subs[runs[r].s0];
+    for (size_t q : singles) {
+      SubGroup& sg = subs[q];
       cr.s_cnt[s_index(sg)]++;
       emit_group(sg, hbit_of(sg));
     }
@@ -785,9 +830,9 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
         const int Lp = popc64(pc.free_mask);
         const bool can_big = Lp >= 12;
         PassHost ph = build_pass(P.comp, tom, masks, pc, n_loc, rb,
-                                 ((opt.cta_mode == 2 && can_big) || Lp >= 13) ? big_caps(Lp) : small_caps());
+                                 ((opt.cta_mode == 2 && can_big) || Lp >= 13) ? big_caps(Lp) : small_caps(), opt.min_bundle, opt.share_weight);
         if (opt.cta_mode == 0 && can_big && !ph.caps.big && (ph.chunks.size() > 1 || ph.n_quad > 0))
-          ph = build_pass(P.comp, tom, masks, pc, n_loc, rb, big_caps(Lp));
+          ph = build_pass(P.comp, tom, masks, pc, n_loc, rb, big_caps(Lp), opt.min_bundle, opt.share_weight);
         P.passes.push_back(std::move(ph));
       }
     }

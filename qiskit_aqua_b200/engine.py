@@ -215,6 +215,15 @@ class PauliSumEngine:
         check(lib().psum_expect_batch(self._h, batch, C.c_void_p(t.data_ptr()), ex, _stream_ptr()))
         return np.array([complex(ex[2 * i], ex[2 * i + 1]) for i in range(batch)])
 
+    def to_dense(self):
+        """Dense matrix of the operator as a [2^n, 2^n] complex128 CUDA tensor (small n only)."""
+        if not torch.cuda.is_available():
+            raise PsumError(_lib.ERR_CUDA, 'no CUDA device available; qiskit_aqua_b200 has no CPU fallback')
+        N = self.n_local_amps
+        out = torch.empty((N, N), dtype=torch.complex128, device='cuda')
+        check(lib().psum_to_dense(self._h, C.c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
     # -- diagonal operators -----------------------------------------------------------------------
     def diag(self):
         d = torch.empty(self.n_local_amps, dtype=torch.float64, device='cuda')
@@ -321,6 +330,33 @@ def _host_ptr(psi_host):
         return t.data_ptr(), t, t.numel()
     a = np.ascontiguousarray(np.asarray(psi_host, dtype=np.complex128)).reshape(-1)
     return a.ctypes.data, a, a.size
+
+
+def expect_multi(engines, psi):
+    """[<psi|H_j|psi>] for several packed operators against one device state with a single host
+    synchronisation (psum_expect_multi)."""
+    engines = list(engines)
+    if not engines:
+        return np.zeros(0, dtype=np.complex128)
+    psi = as_device_state(psi, engines[0].n_local_amps)
+    hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    out = (C.c_double * (2 * len(engines)))()
+    check(lib().psum_expect_multi(hs, len(engines), C.c_void_p(psi.data_ptr()), out, _stream_ptr()))
+    return np.array([complex(out[2 * j], out[2 * j + 1]) for j in range(len(engines))])
+
+
+def pauli_decompose_device(matrix):
+    """W[x, z] = weight(x, z) * (-i)^{popc(x & z)} of a dense 2^n x 2^n matrix (numpy or CUDA tensor),
+    computed on the device (psum_pauli_decompose); returns a [2^n, 2^n] complex128 CUDA tensor."""
+    if not torch.cuda.is_available():
+        raise PsumError(_lib.ERR_CUDA, 'no CUDA device available; qiskit_aqua_b200 has no CPU fallback')
+    m = matrix if isinstance(matrix, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(matrix, dtype=np.complex128))
+    m = m.to(device='cuda', dtype=torch.complex128).contiguous()
+    dim = m.shape[0]
+    n = dim.bit_length() - 1
+    out = torch.empty_like(m)
+    check(lib().psum_pauli_decompose(C.c_void_p(m.data_ptr()), n, C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
 
 
 def nccl_unique_id():

@@ -9,8 +9,8 @@ O(T * 2^n * G_x) assembly that dominates `evaluate_with_statevector`.  Here a Ma
 the Pauli sum: `to_matrix_operator` costs nothing, `evaluate_with_statevector` / `evolve` run on the
 device kernels, and the CSR / dense views are produced on demand (column by column on the device)
 for the small operators whose matrices the reference's tests inspect.  A MatrixOperator made from
-a raw matrix is decomposed once on the host into its Pauli sum with a Walsh-Hadamard transform
-(O(4^n n) instead of the reference's 4^n sparse products, op_converter.py:35-39).
+a raw matrix is decomposed once into its Pauli sum with one Walsh-Hadamard transform per x-mask on
+the device (O(4^n n) instead of the reference's 4^n sparse products, op_converter.py:35-39).
 """
 import copy as _copy
 
@@ -40,15 +40,12 @@ def pauli_decompose(matrix, atol=0.0, diagonal_only=False):
     if n > _DECOMPOSE_MAX_QUBITS and not aqua_globals.massive:
         raise ValueError("decomposing a {}-qubit matrix into 4^{} Pauli weights is exponentially large. "
                          "Set aqua_globals.massive=True if you want to proceed.".format(n, n))
-    idx = np.arange(dim)
-    xs = np.zeros(1, dtype=np.int64) if diagonal_only else idx
-    w = m[idx[None, :], idx[None, :] ^ xs[:, None]].astype(np.complex128)      # w[x, i] = M[i, i^x]
-    h = 1
-    while h < dim:                                                                # WHT along i -> z
-        w = w.reshape(len(xs), dim // (2 * h), 2, h)
-        w = np.stack([w[:, :, 0, :] + w[:, :, 1, :], w[:, :, 0, :] - w[:, :, 1, :]], axis=2)
-        h *= 2
-    w = w.reshape(len(xs), dim) / dim
+    # one Walsh-Hadamard transform per x-mask on the device (psum_pauli_decompose)
+    from .engine import pauli_decompose_device
+    w = pauli_decompose_device(m.astype(np.complex128)).cpu().numpy()
+    xs = np.arange(dim)
+    if diagonal_only:
+        xs, w = xs[:1], w[:1]
     x_idx, z_idx = np.nonzero((w != 0.0) & (np.abs(w) > atol))
     x_mask = xs[x_idx]
     ny = np.array([bin(int(a) & int(b)).count('1') for a, b in zip(x_mask, z_idx)], dtype=np.int64)

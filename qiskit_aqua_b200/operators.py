@@ -565,21 +565,12 @@ class _PauliSumMixin(OperatorBase):
                 "if you want to proceed.".format(method, obj_type, dimensions))
 
     def to_matrix(self, massive=False):
-        """Dense matrix (primitive_ops/pauli_op.py:151-153, list_ops/list_op.py:306-318), produced
-        column by column with the matrix-free device kernel: column j = H e_j.  Meant for the small
+        """Dense matrix (primitive_ops/pauli_op.py:151-153, list_ops/list_op.py:306-318), written by one
+        device kernel: H[i, i ^ x] = D_x(i) per x-group (psum_to_dense).  Meant for the small
         operators the reference's tests inspect; the hot path never builds it."""
-        import torch
         n = self.num_qubits
         self._check_massive('to_matrix', True, n, massive)
-        N = 1 << n
-        eng = self._engine_for()
-        out = torch.empty((N, N), dtype=torch.complex128, device='cuda')      # row j holds column j
-        e = torch.zeros(N, dtype=torch.complex128, device='cuda')
-        for j in range(N):
-            e[j] = 1.0
-            eng.apply(e, out=out[j])
-            e[j] = 0.0
-        return out.t().contiguous().cpu().numpy()
+        return self._engine_for().to_dense().cpu().numpy()
 
     def to_spmatrix(self):
         """scipy CSR of the operator (pauli_op.py:164, list_op.py:320-329); small operators only."""

@@ -115,3 +115,78 @@ def test_lanczos_finds_degenerate_copies():
     eng.set_option('lanczos_probe', 0)
     r0 = eng.lanczos(k=3, tol=1e-12)
     assert abs(r0['evals'][0] - ev[0]) < 1e-9           # the lowest value never needs the probe
+
+
+def test_filter_criterion_on_a_non_diagonal_operator_takes_the_dense_branch():
+    """filter_criterion makes the reference ask for all 2^n pairs (numpy_eigen_solver.py:249-251 ->
+    np.linalg.eig, :171-173).  8 qubits: more pairs than the Lanczos basis holds (used to
+    read out of bounds); the dense device branch returns the full sorted spectrum."""
+    from qiskit_aqua_b200 import NumPyEigensolver, WeightedPauliOperator, Pauli, workloads as W
+    n, x, z, y, c = W.two_local_random(8, 60, seed=8)
+    op = WeightedPauliOperator(paulis=[[cc, Pauli.from_masks(int(xx), int(zz), n)] for xx, zz, cc in zip(x, z, c)])
+    dense = po.ref_to_spmatrix([(complex(cc), po.masks_to_label(int(xx), int(zz), n)) for xx, zz, cc in zip(x, z, c)]).toarray()
+    ref = np.sort(np.linalg.eigvalsh(dense))
+    thr = ref[5] - 1e-9
+    res = NumPyEigensolver(op, k=3, filter_criterion=lambda v, e, aux: e.real >= thr).run()
+    np.testing.assert_allclose(np.real(res.eigenvalues), ref[5:8], atol=1e-9)
+    full = NumPyEigensolver(op, k=1 << n).run()
+    np.testing.assert_allclose(np.real(full.eigenvalues), ref, atol=1e-9)
+    vec = full.eigenstates[0].primitive.cpu().numpy()
+    assert np.linalg.norm(dense @ vec - ref[0] * vec) < 1e-8
+    # k beyond the Lanczos basis but below 2^n - 1
+    some = NumPyEigensolver(op, k=150).run()
+    np.testing.assert_allclose(np.real(some.eigenvalues), ref[:150], atol=1e-9)
+
+
+def test_lanczos_rejects_k_beyond_its_basis():
+    from qiskit_aqua_b200 import PauliSumEngine, PsumError, workloads as W
+    n, x, z, y, c = W.two_local_random(10, 80, seed=2)
+    eng = PauliSumEngine(n, x, z, y, c)
+    with pytest.raises(PsumError):
+        eng.lanczos(k=200)
+    with pytest.raises(PsumError):
+        eng.lanczos(k=1 << n)
+
+
+def test_non_hermitian_sum_small_uses_dense_eig():
+    """Complex weights: the reference's eigs(which='SR') is an Arnoldi method and accepts them; on the
+    device the dense branch does (up to 13 qubits), larger ones raise."""
+    from qiskit_aqua_b200 import AquaError, NumPyEigensolver, WeightedPauliOperator, Pauli, workloads as W
+    n, x, z, y, c = W.random_dense_paulis(5, 40, seed=11, complex_coeffs=True)
+    op = WeightedPauliOperator(paulis=[[cc, Pauli.from_masks(int(xx), int(zz), n)] for xx, zz, cc in zip(x, z, c)])
+    dense = po.ref_to_spmatrix([(complex(cc), po.masks_to_label(int(xx), int(zz), n)) for xx, zz, cc in zip(x, z, c)]).toarray()
+    np.testing.assert_allclose(op.to_opflow().to_matrix(), dense, atol=1e-13)
+    ref = np.linalg.eigvals(dense)
+    ref = ref[np.argsort(ref)]
+    res = NumPyEigensolver(op, k=4).run()
+    np.testing.assert_allclose(res.eigenvalues, ref[:4], atol=1e-9)
+    n2, x, z, y, c = W.random_dense_paulis(15, 30, seed=12, complex_coeffs=True)
+    big = WeightedPauliOperator(paulis=[[cc, Pauli.from_masks(int(xx), int(zz), n2)] for xx, zz, cc in zip(x, z, c)])
+    with pytest.raises(AquaError):
+        NumPyEigensolver(big, k=2).run()
+
+
+def test_diagonal_operator_with_filter_uses_one_device_sort():
+    """MaxCut-style diagonal operator with a filter: the reference sorts the diagonal once (:163-169);
+    here one device sort replaces k = 2^n min-sweeps."""
+    from qiskit_aqua_b200 import NumPyEigensolver, WeightedPauliOperator, Pauli
+    rng = np.random.default_rng(3)
+    n = 12
+    paulis = []
+    for _ in range(40):
+        i, j = sorted(rng.choice(n, 2, replace=False).tolist())
+        paulis.append([float(rng.integers(1, 5)), Pauli.from_masks(0, (1 << i) | (1 << j), n)])
+    op = WeightedPauliOperator(paulis=paulis)
+    diag = np.zeros(1 << n)
+    idx = np.arange(1 << n)
+    for w, p in op.paulis:
+        diag += np.real(w) * (1.0 - 2.0 * (np.bitwise_count((idx & p.z_mask).astype(np.uint64)) & 1).astype(np.float64))
+    ref = np.sort(diag)
+    res = NumPyEigensolver(op, k=5, filter_criterion=lambda v, e, aux: e.real > ref[99]).run()
+    want = ref[ref > ref[99]][:5]
+    np.testing.assert_allclose(np.real(res.eigenvalues), want, atol=1e-12)
+    # complex weights on a diagonal operator: np.sort orders by (real, imag)
+    opc = WeightedPauliOperator(paulis=[[w * (1 + 0.5j), p] for w, p in paulis])
+    resc = NumPyEigensolver(opc, k=3).run()
+    refc = np.sort(diag * (1 + 0.5j))[:3]
+    np.testing.assert_allclose(resc.eigenvalues, refc, atol=1e-12)

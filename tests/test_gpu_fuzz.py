@@ -47,7 +47,7 @@ def test_fuzz_apply_and_expect(seed):
         opts = {'tile_bits': int(rng.integers(11, min(13, n) + 1)), 'low_bits': int(rng.integers(1, 7)),
                 'min_cover': int(rng.integers(1, 5)), 'late_bits': int(rng.integers(0, 3)),
                 'herm_pairing': int(rng.integers(0, 2)), 'reg_bits': int(rng.integers(3, 5)),
-                'cta_mode': int(rng.integers(0, 3))}
+                'cta_mode': int(rng.integers(0, 3)), 'min_bundle': int(rng.choice([2, 3, 5, 255]))}
         if rng.random() < 0.15:
             opts['kernel'] = 1
     psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)

@@ -27,10 +27,11 @@ def same_paulis(got_paulis, want, tol=1e-12):
     assert np.allclose([g[1] for g in got], [w[1] for w in want], rtol=tol, atol=tol)
 
 
-# ---- host side (no device) ----------------------------------------------------------------------
+# ---- matrix -> Pauli sum: one Walsh-Hadamard transform per x-mask on the device ---------------------
+@pytest.mark.gpu
 @pytest.mark.parametrize('rec', FX['decompose'], ids=[r['name'] for r in FX['decompose']])
 def test_matrix_to_pauli_sum_equals_reference(rec):
-    """tr(P M)/2^n by Walsh-Hadamard transform == the reference's 4^n sparse products, same order."""
+    """tr(P M)/2^n by the device Walsh-Hadamard kernel == the reference's 4^n sparse products, same order."""
     mo = MatrixOperator(mat(rec['matrix']))
     assert mo.num_qubits == rec['num_qubits'] and str(mo) == rec['str']
     same_paulis(op_converter.to_weighted_pauli_operator(mo).paulis, rec['paulis'])
@@ -39,6 +40,7 @@ def test_matrix_to_pauli_sum_equals_reference(rec):
     assert np.allclose(po.ref_to_spmatrix(terms).toarray(), mat(rec['matrix']), atol=1e-12)
 
 
+@pytest.mark.gpu
 def test_decompose_options_and_guards():
     m = np.diag([1.0, 2.0, 3.0, 5.0])
     full = pauli_decompose(m)
@@ -56,6 +58,7 @@ def test_decompose_options_and_guards():
         MatrixOperator(None).evaluate_with_statevector(np.ones(2))
 
 
+# ---- host side (no device) ----------------------------------------------------------------------
 def test_converters_do_not_build_a_matrix():
     rec = FX['pauli_sums'][0]
     op = q.WeightedPauliOperator(paulis=[[complex(*w), q.Pauli(l)] for w, l in rec['terms']])

@@ -62,6 +62,8 @@ CASES = [
     (14, 200, {'tile_bits': 11, 'reg_bits': 4}, {'dense': 12}),
     (13, 300, {'tile_bits': 13, 'reg_bits': 4}, {}),
     (12, 600, {'tile_bits': 11, 'reg_bits': 4}, {'no_y': True, 'complex_weights': False}),
+    (12, 800, {'tile_bits': 11, 'min_bundle': 4}, {}),
+    (13, 500, {'tile_bits': 12, 'reg_bits': 4, 'min_bundle': 255}, {'max_weight': 5}),
 ]
 
 
