@@ -53,8 +53,9 @@ struct PassParams {
 // shared memory of one k_pass CTA (bytes), L tile bits
 // layout: [offHi 64 u64][red 16 double2][baseT 9*64 u64][group records][bundle records][patterns] at
 // compile-time offsets (big = one CTA per SM), then the tile (2^L amplitudes), then the quad arena
+constexpr int kChunkSlots = 8;   // chunk records mirrored in shared memory (read every round)
 __host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
-  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
+  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(ChunkRec) * kChunkSlots + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
          sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
 }
 __host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap) {
@@ -68,6 +69,24 @@ __device__ __forceinline__ double flip_sign(double v, int s) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+// loads through 32-bit shared-space addresses: the hot loops keep one base register per array instead
+// of re-deriving the CTA's shared window (S2R SR_CgaCtaId) for every generic pointer
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -162,11 +181,11 @@ __device__ __forceinline__ void perm_fma(double2 (&yacc)[NA], const double2 (&pv
 }
 
 // sum of the (tile-folded, thread-signed) coefficients of `cnt` patterns starting at p
-__device__ __forceinline__ double pattern_sum(const uint4* __restrict__ pat4, int& p, int cnt, uint32_t t0) {
+__device__ __forceinline__ double pattern_sum(uint32_t pat_s, int& p, int cnt, uint32_t t0) {
   double s = 0.0;
 #pragma unroll 4
   for (int j = 0; j < cnt; ++j, ++p) {
-    const uint4 rec = pat4[p];
+    const uint4 rec = lds_u4(pat_s + 16u * (uint32_t)p);
     s += __hiloint2double((int)(rec.y ^ ((uint32_t)(__popc(rec.z & t0)) << 31)), (int)rec.x);
   }
   return s;
@@ -200,13 +219,16 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   uint64_t* offHi = reinterpret_cast<uint64_t*>(smem_raw);
   double2* red = reinterpret_cast<double2*>(offHi + 64);
   uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
-  uint4* grp4 = reinterpret_cast<uint4*>(baseT + 9 * 64);   // 3 x uint4 per group record
+  uint4* chk4 = reinterpret_cast<uint4*>(baseT + 9 * 64);   // the first kChunkSlots chunk records (4 x uint4 each)
+  uint4* grp4 = chk4 + 4 * kChunkSlots;                     // 3 x uint4 per group record
   uint4* bun4 = grp4 + 3 * (GCAP + 1);                      // 1 x uint4 per bundle record
   PatRec* pat = reinterpret_cast<PatRec*>(bun4 + (GCAP + 1));
   double2* tile = reinterpret_cast<double2*>(pat + PCAP);
   double* qtab = reinterpret_cast<double*>(tile + tile_amps);   // tables of the chunk's quadratic groups
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
   const int nW = L - 5 - RB;                                 // warp/round tile bits
+  const uint32_t tile_s = smem_addr(tile), grp_s = smem_addr(grp4), bun_s = smem_addr(bun4), pat_s = smem_addr(pat),
+                 qtab_s = smem_addr(qtab), chk_s = smem_addr(chk4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -229,6 +251,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     for (int j = 0; j < 6 && 6 * k + j < P.n_nonfree; ++j) o |= (uint64_t)((v >> j) & 1) << P.nbit[6 * k + j];
     baseT[e] = o;
   }
+  for (int e = tid; e < 4 * (P.nchunks < kChunkSlots ? P.nchunks : kChunkSlots); e += NT)
+    chk4[e] = reinterpret_cast<const uint4*>(P.chunks)[e];
   __syncthreads();
   const int nrounds = (int)(tile_amps / (NT * NA));
   const int nload = (int)(tile_amps / NT);
@@ -340,7 +364,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                                           : make_double2(0.0, 0.0);
 
       for (int c = 0; c < P.nchunks; ++c) {
-        const ChunkRec ch = P.chunks[c];
+        ChunkRec ch;
+        if (c < kChunkSlots) {
+          uint4* cw = reinterpret_cast<uint4*>(&ch);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 64u * (uint32_t)c + 16u * q);
+        } else {
+          ch = P.chunks[c];
+        }
         if (!one_chunk) {
           __syncthreads();  // everyone is done with the previous chunk's pat / grp
           stage_chunk(ch, base);
@@ -357,12 +388,12 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
             const int XR = s & (NA - 1);   // compile-time after unrolling
 #pragma unroll(kUnroll)
             for (; g < gend; ++g) {
-              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+              const uint4 h0 = lds_u4(grp_s + 48u * (uint32_t)g), hc = lds_u4(grp_s + 48u * (uint32_t)g + 16u);
               if (HERM && (h0.y >> 28) && ((t0 >> ((h0.y >> 28) - 1u)) & 1u)) continue;  // partner half
-              const double2* pp = tile + ((t0 ^ h0.x) & ~((uint32_t)(NA - 1) << 5));
+              const uint32_t pa = tile_s + 16u * ((t0 ^ h0.x) & ~((uint32_t)(NA - 1) << 5));
               double2 pv[NA];
 #pragma unroll
-              for (int r = 0; r < NA; ++r) pv[r] = pp[(r ^ XR) << 5];
+              for (int r = 0; r < NA; ++r) pv[r] = lds_d2(pa + 512u * (uint32_t)(r ^ XR));
               const uint32_t q1 = (uint32_t)__popc(h0.w & t0);
               const uint32_t sg = (h0.y >> (22 + RB)) & 1u;   // slot-1 class = xr: odd r flip its sign
               const double s0 = __hiloint2double((int)(hc.y ^ ((uint32_t)__popc(h0.z & t0) << 31)), (int)hc.x);
@@ -383,7 +414,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         // ---- bundles: one set of partner amplitudes, a register permutation per member ----------
         {
           for (int b = 0; b < ch.nb; ++b) {
-            const uint4 B = bun4[b];
+            const uint4 B = lds_u4(bun_s + 16u * (uint32_t)b);
             int g = (int)(B.y >> 16);
             const int gend = g + (int)(B.y & 0xffu);
             if (HERM) {  // partner half of a paired bundle (warp-uniform)
@@ -392,16 +423,16 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
             }
             double2 pv[NA];
             if (!(B.x >> 31)) {
-              const double2* pp = tile + (t0 ^ B.x);   // register bits clear on both sides
+              const uint32_t pa = tile_s + 16u * (t0 ^ B.x);   // register bits clear on both sides
 #pragma unroll
-              for (int r = 0; r < NA; ++r) pv[r] = pp[r << 5];
+              for (int r = 0; r < NA; ++r) pv[r] = lds_d2(pa + 512u * (uint32_t)r);
             } else {
               const char* pp = reinterpret_cast<const char*>(src + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
 #pragma unroll
               for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
             }
             for (; g < gend; ++g) {
-              const uint4 h0 = grp4[3 * g], hc = grp4[3 * g + 1];
+              const uint4 h0 = lds_u4(grp_s + 48u * (uint32_t)g), hc = lds_u4(grp_s + 48u * (uint32_t)g + 16u);
               const uint32_t var = (h0.y >> 22) & 63u;
               const uint32_t xr = (h0.x >> 5) & (uint32_t)(NA - 1);
               if (var < 2u * NA) {
@@ -427,22 +458,24 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                 }
               } else if (var == (uint32_t)kVarQuad) {
                 // quadratic member: D from the separable tables of this tile
-                const double* qt = qtab + (hc.w >> 16);
-                const int w = (int)(t0 >> (5 + RB)), wsz = 1 << nW;
-                const double* qw = qt + (1 + nW + RB) * 32;
+                const uint32_t qt = qtab_s + 8u * (hc.w >> 16) + 8u * (uint32_t)lane;   // lane tables: [table][lane]
+                const uint32_t w = t0 >> (5 + RB);
+                const uint32_t qw = qtab_s + 8u * (hc.w >> 16) + 256u * (uint32_t)(1 + nW + RB) + 8u * w;   // w tables
+                const uint32_t wsz8 = 8u << nW;
                 double v[NA];
 #pragma unroll
                 for (int m = 0; m < NA; ++m) v[m] = 0.0;
-                double a0 = qt[lane] + qw[w];
+                double a0 = lds_d(qt) + lds_d(qw);
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
-                  if (j < nW) a0 += flip_sign(qt[32 * (1 + j) + lane], (w >> j) & 1);
+                  if (j < nW) a0 += flip_sign(lds_d(qt + 256u * (uint32_t)(1 + j)), (int)((w >> j) & 1u));
                 v[0] = a0;
 #pragma unroll
-                for (int i = 0; i < RB; ++i) v[1 << i] = qt[32 * (1 + nW + i) + lane] + qw[(1 + i) * wsz + w];
+                for (int i = 0; i < RB; ++i)
+                  v[1 << i] = lds_d(qt + 256u * (uint32_t)(1 + nW + i)) + lds_d(qw + wsz8 * (uint32_t)(1 + i));
 #pragma unroll
                 for (int m = 0; m < NA; ++m)
-                  if (__popc(m) == 2) v[m] = qw[(1 + RB) * wsz + m];
+                  if (__popc(m) == 2) v[m] = lds_d(qw - 8u * w + wsz8 * (uint32_t)(1 + RB) + 8u * (uint32_t)m);
                 // Walsh-Hadamard over the register bits: D[r] = sum_m (-1)^{popc(m & r)} v[m]
 #pragma unroll
                 for (int i = 0; i < RB; ++i) {
@@ -462,11 +495,11 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                 }
               } else {
                 // general member: class entry lists
-                const uint4 h2 = grp4[3 * g + 2];
+                const uint4 h2 = lds_u4(grp_s + 48u * (uint32_t)g + 32u);
                 int p = (int)(h0.y & 0xffffu);
                 if ((h0.y >> 21) & 1u) {
                   // flat: one real class-0 entry -> the same D for all amplitudes of the thread
-                  const double sf = pattern_sum(pat4, p, (int)(h2.z & 0x7ffu), t0);
+                  const double sf = pattern_sum(pat_s, p, (int)(h2.z & 0x7ffu), t0);
                   switch (xr) {
 #define PSUM_FLAT_CASE(V) case V: fast_fma<NA, V, false>(yacc, pv, sf, sf); break;
                     PSUM_REP32(PSUM_FLAT_CASE)
@@ -481,7 +514,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                   for (int e = 0; e < nent; ++e) {
                     const uint32_t ent = (uint32_t)ents & 0xffffu;
                     ents >>= 16;
-                    const double sc = pattern_sum(pat4, p, (int)(ent & 0x7ffu), t0);
+                    const double sc = pattern_sum(pat_s, p, (int)(ent & 0x7ffu), t0);
                     switch (ent >> 11) {
 #define PSUM_CLASS_CASE(C) case C: add_class<NA, C, ND>(D, sc); break;
                       PSUM_REP32(PSUM_CLASS_CASE)
@@ -513,7 +546,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         if (EXPECT) {
           const double2 b = bra ? __ldg(reinterpret_cast<const double2*>(
                                       reinterpret_cast<const char*>(bra + i0) + P.roff[r]))
-                                : tile[t0 | ((uint32_t)r << 5)];
+                                : lds_d2(tile_s + 16u * (t0 | ((uint32_t)r << 5)));
           eacc.x += b.x * yacc[r].x + b.y * yacc[r].y;
           eacc.y += b.x * yacc[r].y - b.y * yacc[r].x;
         }
