@@ -270,13 +270,16 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch.b0)[b];
     if (tid < 3) grp4[ch.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
     if (tid == 3) bun4[ch.nb] = make_uint4(0u, 0u, 0u, 0u);
+    // long term lists (a pattern that collects, e.g., every Z_a Z_b with both qubits outside the
+    // tile) are deferred to a queue and folded by a whole warp each: one lane looping over a hundred
+    // terms would stall its warp -- and with it the CTA -- at the next barrier
+    int* lq_count = reinterpret_cast<int*>(red);
+    uint16_t* lq = reinterpret_cast<uint16_t*>(red) + 8;
+    constexpr int kLongCap = 120;
+    const bool has_long = (ch.q0 >> 31) != 0;
+    if (tid == 4) *lq_count = 0;
     __syncthreads();
-    for (int p = tid; p < ch.np; p += NT) {
-      const int gp = ch.p0 + p;
-      const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
-      double v = 0.0;
-      for (uint32_t t = ta; t < tb; ++t)
-        v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+    auto put_pattern = [&](int p, int gp, double v) {
       const uint32_t zraw = P.pat_zt[gp];
       if (HERM && (zraw & 0x8000u)) v += v;
       uint4 rec;
@@ -288,6 +291,35 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       const uint32_t inl = P.pat_inl[gp];
       if (inl != 0xffffu)
         reinterpret_cast<double*>(grp4 + 3 * (inl >> 1) + 1)[inl & 1u] = v;
+    };
+    for (int p = tid; p < ch.np; p += NT) {
+      const int gp = ch.p0 + p;
+      const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
+      if (has_long && tb - ta > (uint32_t)kLongTerms) {
+        const int k = atomicAdd(lq_count, 1);
+        if (k < kLongCap) {
+          lq[k] = (uint16_t)p;
+          continue;
+        }
+      }
+      double v = 0.0;
+      for (uint32_t t = ta; t < tb; ++t)
+        v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+      put_pattern(p, gp, v);
+    }
+    if (has_long) {
+      __syncthreads();
+      const int nlong = *lq_count < kLongCap ? *lq_count : kLongCap;
+      for (int li = warp; li < nlong; li += NT / 32) {
+        const int p = (int)lq[li], gp = ch.p0 + p;
+        const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
+        double v = 0.0;
+        for (uint32_t t = ta + (uint32_t)lane; t < tb; t += 32u)
+          v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) put_pattern(p, gp, v);
+      }
     }
     if (ch.nq) {
       // quadratic groups: rebuild the separable tables of this tile from the folded patterns.
@@ -297,7 +329,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       const int nlt = 1 + nW + RB, ntab = nlt + 1 + RB + 1;
       for (int task = warp; task < (int)ch.nq * ntab; task += NT / 32) {
         const int qi = task / ntab, tb = task - qi * ntab;
-        const int g = (int)P.quad_idx[ch.q0 + qi];
+        const int g = (int)P.quad_idx[(ch.q0 & 0x7fffffffu) + qi];
         const uint32_t meta = reinterpret_cast<const uint32_t*>(grp4 + 3 * g)[1];
         const uint8_t* area = reinterpret_cast<const uint8_t*>(grp4 + 3 * g) + 8;
         double* qt = qtab + (int)*reinterpret_cast<const uint16_t*>(area + 22);

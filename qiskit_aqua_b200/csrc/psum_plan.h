@@ -90,7 +90,8 @@ struct ChunkRec {  // 64 bytes
                    // bundle.  They need no bundle record and are sorted by s = im*NA + xr so that each
                    // (im, xr) runs its own straight-line loop with a compile-time register permutation
   uint16_t nq;     // quadratic groups in the chunk (their tables are rebuilt per tile)
-  uint32_t q0;     // their group indices (inside the chunk): quad_idx[q0 .. q0 + nq)
+  uint32_t q0;     // bits 0..30: their group indices (inside the chunk) are quad_idx[q0 .. q0 + nq);
+                   // bit 31: some pattern of the chunk sums more than kLongTerms terms (warp-cooperative fold)
   uint8_t s_cnt[32];  // singles per s
 };
 static_assert(sizeof(ChunkRec) == 64, "ChunkRec layout");
@@ -99,6 +100,7 @@ constexpr int kMaxTileBits = 13;
 constexpr int kRegBitLo = 5;     // tile bits 5 .. 5+RB-1 live in registers (2^RB amplitudes per thread)
 constexpr int kVarGeneral = 63;
 constexpr int kVarQuad = 62;
+constexpr int kLongTerms = 24;   // a pattern with more terms is folded by a whole warp
 // "Quadratic" groups: every in-tile z-pattern is real and touches at most two tile bits (ZZ couplings,
 // Z X Z decorations, ...).  D(lane, w, r) of such a group is a quadratic form in the signs of the tile
 // bits; it separates into small tables over the lane bits and over the warp/round bits that are
@@ -690,6 +692,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     });
     int pl = 0, gl = 0;
     int nq_emitted = 0;
+    bool has_long = false;
     auto emit_group = [&](SubGroup& sg, uint32_t hbit) {
       sg.G.meta |= (uint32_t)pl | (hbit << 28);
       const bool is_quad = sg.var == kVarQuad;
@@ -700,6 +703,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
         ++nq_emitted;
       }
       for (size_t j = 0; j < sg.pats.size(); ++j) {
+        if ((int)sg.pats[j].terms.size() > kLongTerms) has_long = true;
         // bit 15 of the stored pattern marks patterns of a Hermitian-paired bundle (doubled by the
         // fold of the Hermitian expectation kernels, masked off by every fold)
         P.pat_zt.push_back((uint16_t)(sg.pats[j].zt | (hbit ? 0x8000u : 0u)));
@@ -744,6 +748,7 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     cr.np = pl;
     cr.nb = (int32_t)P.bundles.size() - cr.b0;
     cr.nq = (uint16_t)nq_emitted;
+    if (has_long) cr.q0 |= 0x80000000u;
     P.chunks.push_back(cr);
     g0 += gl;
     p0 += pl;

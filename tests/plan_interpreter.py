@@ -246,7 +246,10 @@ def run_pass(ps, src, y=None, herm=False, check=True):
                     g += 1
             assert g == ns
             if check:       # the chunk's quadratic groups are listed in quad_idx[q0 : q0 + nq)
-                listed = [int(v) for v in ps['quad_idx'][int(ch['q0']):int(ch['q0']) + int(ch['nq'])]]
+                q0 = int(ch['q0']) & 0x7fffffff
+                listed = [int(v) for v in ps['quad_idx'][q0:q0 + int(ch['nq'])]]
+                longest = max([int(ps['pat_tptr'][p0 + q + 1]) - int(ps['pat_tptr'][p0 + q]) for q in range(npat)] or [0])
+                assert (int(ch['q0']) >> 31) == (1 if longest > 24 else 0)
                 actual = [gi for gi in range(ng) if (int(grp[gi]['meta']) >> 22) & 63 == VAR_QUAD]
                 assert listed == actual
             seen = ns
