@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument('--cta-mode', type=int, default=-1)
     ap.add_argument('--min-bundle', type=int, default=0)
     ap.add_argument('--share-weight', type=int, default=-1)
+    ap.add_argument('--comm-sms', type=int, default=-1)
+    ap.add_argument('--peer-copy', type=int, default=-1)
     return ap.parse_args()
 
 
@@ -287,6 +289,10 @@ def main():
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.shard(rank, world, uid[0])
+    if args.comm_sms >= 0:
+        eng.set_option('comm_sms', args.comm_sms)
+    if args.peer_copy >= 0:
+        eng.set_option('peer_copy', args.peer_copy)
     info = eng.info()
     gx_total = info['n_xgroups']
 

@@ -63,6 +63,7 @@ struct NcclApi {
   int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -70,6 +71,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;
+constexpr int kNcclUint8 = 1;  // ncclUint8
 
 int load_nccl() {
   if (g_nccl.lib) return PSUM_OK;
@@ -83,10 +85,22 @@ int load_nccl() {
 #define LOAD(sym)                                                              \
   *(void**)(&g_nccl.sym) = dlsym(lib, "nccl" #sym);                             \
   if (!g_nccl.sym) return fail(PSUM_ERR_NCCL, "libnccl lacks symbol nccl" #sym);
-  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(AllReduce)
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(AllReduce) LOAD(AllGather)
   LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
 #undef LOAD
   g_nccl.lib = lib;
+  return PSUM_OK;
+}
+// cuMemGetAddressRange (driver API, through dlopen): base of the allocation a device pointer lives in
+typedef int (*cu_get_range_t)(unsigned long long*, size_t*, unsigned long long);
+cu_get_range_t g_cu_get_range = nullptr;
+int load_cuda_driver() {
+  if (g_cu_get_range) return PSUM_OK;
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(PSUM_ERR_CUDA, "cannot dlopen libcuda.so.1: %s", dlerror());
+  *(void**)(&g_cu_get_range) = dlsym(lib, "cuMemGetAddressRange_v2");
+  if (!g_cu_get_range) return fail(PSUM_ERR_CUDA, "libcuda lacks cuMemGetAddressRange_v2");
   return PSUM_OK;
 }
 #define NCCL_TRY(expr)                                                                        \
@@ -154,6 +168,13 @@ struct psum_handle_s {
   // exchange instrumentation (option "profile_exchange") and the compute-only mode used to measure
   // how much of the exchange hides behind the passes (option "skip_exchange")
   int profile_exchange = 0, skip_exchange = 0;
+  // peer-memory exchange: every rank maps its partners' source vector through CUDA IPC and PULLS the
+  // partner shard with the copy engines (no SM is taken from the passes); NCCL send/recv is the fallback
+  int peer_copy = 1;        // option "peer_copy": 1 = copy engines over IPC-mapped peer memory, 0 = NCCL send/recv
+  std::vector<std::pair<std::string, void*>> ipc_open;   // opened peer allocations (handle bytes -> base)
+  void* d_ipc = nullptr;    // device scratch of the handle all-gather (world x 80 bytes)
+  int comm_sms = 0;         // SMs left to the NCCL send/recv kernels while exchanges are in flight
+  int grid_reserve = 0;     // (set by the sharded driver) SMs the pass launches leave free
   std::vector<cudaEvent_t> ex_ev;   // start/stop pairs on comm_stream
   int ex_count = 0;
   double ex_stats[4] = {0, 0, 0, 0};
@@ -359,6 +380,9 @@ extern "C" int psum_destroy(psum_handle_t h) {
   }
   for (auto& ev : h->ex_ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& kv : h->ipc_open)
+    if (kv.second) cudaIpcCloseMemHandle(kv.second);
+  if (h->d_ipc) cudaFree(h->d_ipc);
   for (auto& ev : h->ev_chunk)
     if (ev) cudaEventDestroy(ev);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
@@ -411,6 +435,13 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
     return PSUM_OK;
   } else if (k == "skip_exchange") {
     h->skip_exchange = value ? 1 : 0;
+    return PSUM_OK;
+  } else if (k == "peer_copy") {
+    h->peer_copy = value ? 1 : 0;
+    return PSUM_OK;
+  } else if (k == "comm_sms") {
+    if (value < 0 || value > 64) return fail(PSUM_ERR_INVALID, "comm_sms must be 0..64");
+    h->comm_sms = (int)value;
     return PSUM_OK;
   } else if (k == "copy_threads") {
     if (value < 0 || value > 256) return fail(PSUM_ERR_INVALID, "copy_threads must be 0..256");
@@ -593,11 +624,18 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
         pp.tile_end = pp.tile_begin + per;
       }
       pp.accumulate = (accumulate || pi > 0) ? 1 : 0;
+      // the persistent grid fills every SM; while an exchange is in flight a few SMs are left to the
+      // NCCL kernels, otherwise CTAs that cannot become resident wait for a whole pass
+      int grid = dp.grid;
+      if (h->grid_reserve > 0) {
+        const int per_sm = std::max(1, dp.grid / std::max(1, h->num_sms));
+        grid = std::max(per_sm, std::min(dp.grid, (h->num_sms - h->grid_reserve) * per_sm));
+      }
       const bool last = last_part && (pi + 1 == D.passes.size());
       const bool ex = want_expect && (y ? last : true);
       double2* part = ex ? h->d_partial + *pcount : nullptr;
       const double2* b = bra_is_src ? nullptr : bra;
-      if (ex && *pcount + dp.grid > h->partial_cap)
+      if (ex && *pcount + grid > h->partial_cap)
         return fail(PSUM_ERR_NOMEM, "expectation partial buffer too small");
       // Hermitian pairing: expectation only, <psi|H|psi> of a Hermitian operator, local part
       const bool herm = !y && h->hermitian && h->herm_pairing && bra_is_src && D.g == 0;
@@ -605,15 +643,15 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
                        ((herm && ex) ? kModeHerm : 0);
       cudaError_t le;
       if (dp.rb == 4)
-        le = dp.threads == 256 ? kpass_launch_4_256(mode, dp.grid, dp.smem, st, src, b, y, pp, part)
-                               : kpass_launch_4_128(mode, dp.grid, dp.smem, st, src, b, y, pp, part);
+        le = dp.threads == 256 ? kpass_launch_4_256(mode, grid, dp.smem, st, src, b, y, pp, part)
+                               : kpass_launch_4_128(mode, grid, dp.smem, st, src, b, y, pp, part);
       else
-        le = dp.threads == 512 ? kpass_launch_3_512(mode, dp.grid, dp.smem, st, src, b, y, pp, part)
-                               : kpass_launch_3_256(mode, dp.grid, dp.smem, st, src, b, y, pp, part);
+        le = dp.threads == 512 ? kpass_launch_3_512(mode, grid, dp.smem, st, src, b, y, pp, part)
+                               : kpass_launch_3_256(mode, grid, dp.smem, st, src, b, y, pp, part);
       if (le != cudaSuccess)
         return fail(PSUM_ERR_CUDA, "k_pass launch (mode %d, rb %d, %d threads) failed: %s", mode, dp.rb, dp.threads,
                     cudaGetErrorString(le));
-      if (ex) *pcount += dp.grid;
+      if (ex) *pcount += grid;
     }
   } else {
     const bool ex = want_expect && (y ? last_part : true);
@@ -1200,6 +1238,75 @@ static int host_late_bits(const psum_handle_s* h) {
   return std::max(0, std::min(4, h->n_loc - std::max(11, std::min(h->opt.tile_bits, kMaxTileBits))));
 }
 
+// Peer pointers of the source vector: every rank exports the allocation that holds its `psi` through
+// CUDA IPC, the (handle, offset) records are all-gathered over NCCL, and the partners' allocations are
+// opened (cached).  peers[r] = device pointer, valid on THIS device, of rank r's shard.  Returns
+// PSUM_OK with peers empty when IPC is not available for this buffer (the caller falls back to NCCL).
+static int resolve_peers(psum_handle_s* h, const void* psi_dev, std::vector<const double2*>* peers) {
+  peers->clear();
+  struct Rec {
+    cudaIpcMemHandle_t handle;
+    unsigned long long offset;
+    unsigned long long ok;
+  };
+  static_assert(sizeof(Rec) == 80, "IPC record layout");
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  if (load_cuda_driver() == PSUM_OK) {
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (g_cu_get_range(&base, &size, (unsigned long long)(uintptr_t)psi_dev) == 0 &&
+        cudaIpcGetMemHandle(&mine.handle, (void*)(uintptr_t)base) == cudaSuccess) {
+      mine.offset = (unsigned long long)(uintptr_t)psi_dev - base;
+      mine.ok = 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (!h->d_ipc) CUDA_TRY(cudaMalloc(&h->d_ipc, sizeof(Rec) * (size_t)(h->world + 1)));
+  std::vector<Rec> all((size_t)h->world);
+  char* d = (char*)h->d_ipc;
+  CUDA_TRY(cudaMemcpyAsync(d + sizeof(Rec) * h->world, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->comm_stream));
+  NCCL_TRY(g_nccl.AllGather(d + sizeof(Rec) * h->world, d, sizeof(Rec), kNcclUint8, h->comm, h->comm_stream));
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d, sizeof(Rec) * h->world, cudaMemcpyDeviceToHost, h->comm_stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  for (int r = 0; r < h->world; ++r)
+    if (!all[r].ok) return PSUM_OK;   // some rank cannot export: everybody falls back
+  peers->resize((size_t)h->world, nullptr);
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) {
+      (*peers)[r] = (const double2*)psi_dev;
+      continue;
+    }
+    const std::string key((const char*)&all[r].handle, sizeof(cudaIpcMemHandle_t));
+    void* base = nullptr;
+    for (auto& kv : h->ipc_open)
+      if (kv.first == key) base = kv.second;
+    if (!base) {
+      cudaError_t e = cudaIpcOpenMemHandle(&base, all[r].handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        peers->clear();
+        // the decision must be the same on every rank: agree through the flag all-reduce below
+        base = nullptr;
+      } else {
+        h->ipc_open.emplace_back(key, base);
+      }
+    }
+    if (peers->empty()) break;
+    (*peers)[r] = (const double2*)((const char*)base + all[r].offset);
+  }
+  // all ranks must take the same path
+  double flag = peers->empty() ? 1.0 : 0.0;
+  double* dflag = (double*)h->d_ipc;
+  CUDA_TRY(cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, h->comm_stream));
+  NCCL_TRY(g_nccl.AllReduce(dflag, dflag, 1, kNcclFloat64, kNcclSum, h->comm, h->comm_stream));
+  CUDA_TRY(cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, h->comm_stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  if (flag != 0.0) peers->clear();
+  return PSUM_OK;
+}
+
 // Sharded H.psi / <psi|H|psi>.  host_src != NULL: this rank's shard comes from host memory (y must
 // be NULL): the H2D copy is chunked on the copy stream, the chunk-local passes of the local part
 // follow it chunk by chunk, and the exchanges start when the last chunk has landed.
@@ -1218,6 +1325,8 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     if (!h->comm) return fail(PSUM_ERR_NCCL, "terms with global x-parts need a communicator");
     if (!recv_dev || recv_amps < N) return fail(PSUM_ERR_INVALID, "recv_dev must hold one shard");
   }
+  std::vector<const double2*> peers;
+  if (any_remote && h->peer_copy && !h->skip_exchange) PS_TRY(resolve_peers(h, psi_dev, &peers));
   // ring of receive buffers: up to nbuf exchanges are in flight ahead of the part being computed
   const int nbuf = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, recv_amps / std::max<uint64_t>(N, 1)));
   size_t pcount = 0;
@@ -1262,6 +1371,10 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
   if (any_remote) {
     CUDA_TRY(cudaEventRecord(h->ev_ready, st));   // st has waited for every chunk by now
     CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+    // pulling needs the PARTNER's source vector to be complete: a one-word all-reduce on the
+    // communication streams is the cross-rank "psi is ready" barrier (send/recv pairs imply it)
+    if (!peers.empty())
+      NCCL_TRY(g_nccl.AllReduce(h->d_ipc, h->d_ipc, 1, kNcclFloat64, kNcclSum, h->comm, h->comm_stream));
   }
   auto post_exchange = [&](const DevPart* D, int s, bool must_wait_used) -> int {
     if (must_wait_used) CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_used[s], 0));
@@ -1275,7 +1388,10 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
       }
       CUDA_TRY(cudaEventRecord(h->ex_ev[2 * h->ex_count], h->comm_stream));
     }
-    if (!h->skip_exchange) {
+    if (!h->skip_exchange && !peers.empty()) {
+      // pull the partner shard with the copy engines over NVLink
+      CUDA_TRY(cudaMemcpyAsync(buf, peers[(size_t)peer], N * sizeof(double2), cudaMemcpyDeviceToDevice, h->comm_stream));
+    } else if (!h->skip_exchange) {
       NCCL_TRY(g_nccl.GroupStart());
       NCCL_TRY(g_nccl.Send(psi, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
       NCCL_TRY(g_nccl.Recv(buf, 2 * N, kNcclFloat64, peer, h->comm, h->comm_stream));
@@ -1290,6 +1406,11 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
   };
   size_t posted = 0;
   h->ex_count = 0;
+  struct ReserveGuard {
+    psum_handle_s* h;
+    ~ReserveGuard() { h->grid_reserve = 0; }
+  } reserve_guard{h};
+  h->grid_reserve = (any_remote && !h->skip_exchange) ? h->comm_sms : 0;
   for (; posted < remote.size() && posted < (size_t)nbuf; ++posted)
     PS_TRY(post_exchange(remote[posted], (int)(posted % nbuf), false));
   // (rest of the) local part: overlaps the exchanges posted above
@@ -1311,6 +1432,10 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
       ++posted;
     }
   }
+  // a partner may still be pulling this rank's psi: nobody leaves before every rank has consumed its
+  // pulls (with an expectation the all-reduce below is that barrier)
+  if (!peers.empty() && !expect_out)
+    NCCL_TRY(g_nccl.AllReduce(h->d_scalar + 128, h->d_scalar + 128, 1, kNcclFloat64, kNcclSum, h->comm, st));
   if (expect_out) {
     k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
     CUDA_TRY(cudaGetLastError());
