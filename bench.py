@@ -309,9 +309,10 @@ def main():
     nrm2 = allreduce(vec_dot(psi, psi).real)
     if world > 1 and info['n_global_parts'] > 0:
         free_b, _ = torch.cuda.mem_get_info()
-        # two exchange buffers: more were measured to bring nothing (the exchanges already hide
-        # behind the local part) and only raise the memory footprint
-        nbuf = 2 if free_b > 3.2 * 16 * N_loc else 1
+        # one receive buffer per exchanged shard when memory allows (the partner shards are pulled by
+        # the copy engines while the local part runs, so every pull can complete behind it); the ring
+        # works with any count >= 1.  One shard of head-room stays free for the e2e scratch.
+        nbuf = int(max(1, min(info['n_global_parts'], (free_b - 1.5 * 16 * N_loc) // (16 * N_loc))))
         recv = torch.empty(nbuf * N_loc, dtype=torch.complex128, device='cuda')
     scale = 1.0 / np.sqrt(nrm2)
     vec_scale(psi, scale)
@@ -544,6 +545,7 @@ def main():
                        'patterns': info['n_patterns'], 'remote_groups': info['n_remote_groups'],
                        'tile_bits': info['tile_bits'], 'reg_bits': args.reg_bits or 3,
                        'sharding': 'top %d qubits' % p_bits, 'global_parts': info['n_global_parts'],
+                       'recv_buffers': (recv.numel() // N_loc) if recv is not None else 0,
                        'l2': 'inputs (%.0f GiB per GPU) larger than L2' % (16 * N_loc / 2 ** 30)},
             'energy': energy.real if energy is not None else None,
             'clocks': clk.summary(), 'gpu_launches': launches, 'roofline': roofline}
