@@ -190,3 +190,29 @@ def test_diagonal_operator_with_filter_uses_one_device_sort():
     resc = NumPyEigensolver(opc, k=3).run()
     refc = np.sort(diag * (1 + 0.5j))[:3]
     np.testing.assert_allclose(resc.eigenvalues, refc, atol=1e-12)
+
+
+def test_config4_lanczos_ground_state_tol_1e12():
+    """BASELINE config 4: 30-qubit TFIM + Heisenberg + 3-local Hamiltonian, 10 000 terms,
+    on-device Lanczos ground state at tol = 1e-12.  The explicit residual |H v - E v| and the Rayleigh
+    quotient of the returned vector are recomputed with independent kernel launches.  (About 200
+    matvecs of ~0.35 s plus the second pass for the vector: ~2.5 minutes on a B200; smaller devices
+    run the same operator family at fewer qubits.)"""
+    from qiskit_aqua_b200.engine import vec_dot
+    free_b, _ = torch.cuda.mem_get_info()
+    n = 30 if free_b > 120 * 2 ** 30 else 26
+    pairs = n * (n - 1) // 2
+    _, x, z, y, c = W.ising_heisenberg(n, n_triples=max(0, 10000 - 3 * pairs - n), seed=30)
+    eng = PauliSumEngine(n, x, z, y, c)
+    r = eng.lanczos(k=1, tol=1e-12, max_iter=600, seed=4, want_vectors=True)
+    v = r['evecs'][0]
+    e0 = float(r['evals'][0])
+    hv = eng.apply(v)
+    rayleigh = vec_dot(v, hv).real
+    hv.add_(v, alpha=-e0)
+    resid = float(torch.linalg.vector_norm(hv).item())
+    assert abs(float(torch.linalg.vector_norm(v).item()) - 1.0) < 1e-12
+    assert resid <= 1e-8, resid
+    assert abs(rayleigh - e0) <= 1e-10 * abs(e0), (rayleigh, e0)
+    if n == 30:
+        assert abs(e0 - (-35.90543862024841)) < 1e-8       # profiles/config4_lanczos_r2_q30_tol1e-12.json

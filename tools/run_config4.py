@@ -23,7 +23,7 @@ def main():
     eng = PauliSumEngine(n, x, z, y, c)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    r = eng.lanczos(k=1, tol=tol, max_iter=400, seed=4, want_vectors=True)
+    r = eng.lanczos(k=1, tol=tol, max_iter=600, seed=4, want_vectors=True)
     torch.cuda.synchronize()
     t_total = time.perf_counter() - t0
     v = r['evecs'][0]
