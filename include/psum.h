@@ -168,6 +168,13 @@ int psum_gate_1q(void* psi_dev, int n_qubits, int q, const double* u_re_im, psum
 /* kind 0 = CX(control, target), 1 = CZ(control, target). */
 int psum_gate_2q(void* psi_dev, int n_qubits, int kind, int control, int target, psum_stream_t stream);
 
+/* A block of gates whose qubits fit one shared-memory tile (n_free <= 12 qubits, ascending; 0, 1, 2
+ * first when n_qubits >= 3): ONE sweep of the state for the whole block instead of one per gate.
+ * gates_host: n_gates records of 80 bytes {int32 kind (0 = 2x2 unitary on a, 1 = CX control b target
+ * a, 2 = CZ), int32 a, int32 b, int32 pad, double u[8]} with a, b positions inside free_qubits. */
+int psum_gate_block(void* psi_dev, int n_qubits, const int32_t* free_qubits, int n_free,
+                    const void* gates_host, int n_gates, psum_stream_t stream);
+
 /* ---- vector helpers used by the host-side callers (device pointers, complex128) -------- */
 /* Counter-based synthetic state: psi[i] = gauss(seed, first_index + i); its CPU twin is
  * oracle/psum_oracle.c:psum_oracle_state.  Not normalised. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     'psum_state_basis': (C.c_int, [_vp, C.c_int, C.c_uint64, _vp]),
     'psum_gate_1q': (C.c_int, [_vp, C.c_int, C.c_int, _dp, _vp]),
     'psum_gate_2q': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'psum_gate_block': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int32), C.c_int, _vp, C.c_int, _vp]),
     'psum_fill_state': (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp]),
     'psum_vec_dot': (C.c_int, [_vp, _vp, C.c_uint64, _dp, _vp]),
     'psum_vec_scale': (C.c_int, [_vp, C.c_uint64, C.c_double, C.c_double, _vp]),

@@ -70,29 +70,125 @@ class StatevectorCircuit:
     def cz(self, c, t):
         return self._add('cz', [c, t])
 
-    def run(self, params=None, out=None):
-        """Executes on |0...0> and returns the complex128 CUDA state tensor."""
-        n = self.num_qubits
+    # -- execution ------------------------------------------------------------------------------------
+    def _bound_gates(self, params):
+        """[(name, qubits, 2x2 matrix or None)] with the parameters bound."""
         if params is None:
             params = []
         if len(params) != self.num_parameters:
             raise ValueError('expected %d parameters, got %d' % (self.num_parameters, len(params)))
+        out = []
+        for name, qs, val in self.gates:
+            if name in ('cx', 'cz'):
+                out.append((name, qs, None))
+                continue
+            theta = 0.0 if val is None else (params[val[1]] if isinstance(val, tuple) else val)
+            out.append((name, qs, np.asarray(_u(name, float(theta)), dtype=np.complex128)))
+        return out
+
+    def run_unfused(self, params=None, out=None):
+        """Gate by gate: one sweep of the state per gate (psum_gate_1q / psum_gate_2q)."""
+        n = self.num_qubits
         if out is None:
             out = torch.empty(1 << n, dtype=torch.complex128, device='cuda')
         L = lib()
         ptr, st = C.c_void_p(out.data_ptr()), _stream_ptr()
         check(L.psum_state_basis(ptr, n, 0, st))
         buf = (C.c_double * 8)()
-        for name, qs, val in self.gates:
-            if name in ('cx', 'cz'):
+        for name, qs, u in self._bound_gates(params):
+            if u is None:
                 check(L.psum_gate_2q(ptr, n, 0 if name == 'cx' else 1, qs[0], qs[1], st))
                 continue
-            theta = 0.0 if val is None else (params[val[1]] if isinstance(val, tuple) else val)
-            u = np.asarray(_u(name, float(theta)), dtype=np.complex128).reshape(4)
+            u = u.reshape(4)
             for i in range(4):
                 buf[2 * i], buf[2 * i + 1] = u[i].real, u[i].imag
             check(L.psum_gate_1q(ptr, n, qs[0], buf, st))
         return out
+
+    def run(self, params=None, out=None, max_block_qubits=12):
+        """Executes on |0...0> and returns the complex128 CUDA state tensor.  The gate list is cut into
+        blocks whose qubits fit one shared-memory tile (fuse_schedule); each block costs ONE sweep of
+        the state (psum_gate_block) instead of one per gate."""
+        n = self.num_qubits
+        if out is None:
+            out = torch.empty(1 << n, dtype=torch.complex128, device='cuda')
+        L = lib()
+        ptr, st = C.c_void_p(out.data_ptr()), _stream_ptr()
+        check(L.psum_state_basis(ptr, n, 0, st))
+        blocks = fuse_schedule(n, self._bound_gates(params), max_block_qubits)
+        self.last_block_count = len(blocks)
+        for free, gates in blocks:
+            pos = {q: j for j, q in enumerate(free)}
+            recs = np.zeros(len(gates), dtype=GATE_DT)
+            for k, (name, qs, u) in enumerate(gates):
+                if u is None:
+                    recs[k]['kind'] = 1 if name == 'cx' else 2
+                    recs[k]['b'], recs[k]['a'] = pos[qs[0]], pos[qs[1]]      # (control, target)
+                else:
+                    recs[k]['kind'] = 0
+                    recs[k]['a'] = pos[qs[0]]
+                    recs[k]['u'] = u.reshape(4).view(np.float64)
+            fq = (C.c_int32 * len(free))(*free)
+            check(L.psum_gate_block(ptr, n, fq, len(free), recs.ctypes.data_as(C.c_void_p), len(gates), st))
+        return out
+
+
+GATE_DT = np.dtype([('kind', '<i4'), ('a', '<i4'), ('b', '<i4'), ('pad', '<i4'), ('u', '<f8', (8,))])
+assert GATE_DT.itemsize == 80
+
+
+def fuse_schedule(n, gates, max_block_qubits=12):
+    """Cuts a gate list [(name, qubits, matrix)] into blocks [(free_qubits, gates)].
+
+    Consecutive one-qubit gates on a qubit are first merged into one 2x2 matrix.  A block then
+    collects, in program order, every gate whose qubits still fit the block's free set (at most
+    max_block_qubits qubits, always containing the three lowest ones so that the tile is read in
+    128-byte runs); a gate that does not fit blocks its qubits, and every later gate touching a blocked
+    qubit waits for a later block -- gates on disjoint qubits commute, so program order is preserved
+    wherever it matters."""
+    merged = []
+    last_1q = {}                      # qubit -> index in merged of a trailing one-qubit gate
+    for name, qs, u in gates:
+        if u is not None:
+            q = qs[0]
+            if q in last_1q:
+                k = last_1q[q]
+                merged[k] = ('u', (q,), u @ merged[k][2])
+            else:
+                last_1q[q] = len(merged)
+                merged.append(('u', (q,), u))
+        else:
+            for q in qs:
+                last_1q.pop(q, None)
+            merged.append((name, tuple(qs), None))
+    low = list(range(min(3, n)))
+    L = min(max(max_block_qubits, 5), 12, n)      # 3 fixed low qubits + room for any two-qubit gate
+    blocks = []
+    pending = merged
+    while pending:
+        free, blocked, block, rest = set(low), set(), [], []
+        for g in pending:
+            qs = set(g[1])
+            if qs & blocked:
+                blocked |= qs
+                rest.append(g)
+                continue
+            need = qs - free
+            if len(free) + len(need) <= L:
+                free |= need
+                block.append(g)
+            else:
+                blocked |= qs
+                rest.append(g)
+        for q in range(n):              # pad the tile with the lowest unused qubits
+            if len(free) >= L:
+                break
+            free.add(q)
+        if not block:
+            raise RuntimeError('fuse_schedule made no progress')       # cannot happen for L >= min(5, n)
+        blocks.append((sorted(free), block))
+        pending = rest
+    return blocks
 
 
 def _entangler_pairs(n, entanglement):

@@ -1099,6 +1099,66 @@ extern "C" int psum_gate_2q(void* psi_dev, int n_qubits, int kind, int control, 
   return PSUM_OK;
 }
 
+// A block of gates on at most 12 qubits in one HBM sweep (the tile of the block's qubits is staged in
+// shared memory).  free_qubits: the L block qubits, ascending; when n_qubits >= 3 they must start with
+// 0, 1, 2 (128-byte runs).  gates_host: n_gates records of 80 bytes {int32 kind, a, b, pad; double u[8]}
+// with a, b = positions INSIDE free_qubits (tile bits).
+extern "C" int psum_gate_block(void* psi_dev, int n_qubits, const int32_t* free_qubits, int n_free,
+                               const void* gates_host, int n_gates, psum_stream_t stream) {
+  if (!psi_dev || !free_qubits || !gates_host || n_gates < 1) return fail(PSUM_ERR_INVALID, "bad argument");
+  if (n_qubits < 1 || n_qubits > 40 || n_free < 1 || n_free > 12 || n_free > n_qubits)
+    return fail(PSUM_ERR_INVALID, "gate block: 1 <= n_free <= min(12, n_qubits)");
+  GateBlockParams P;
+  memset(&P, 0, sizeof(P));
+  uint64_t fm = 0;
+  for (int j = 0; j < n_free; ++j) {
+    const int q = free_qubits[j];
+    if (q < 0 || q >= n_qubits || (j > 0 && q <= free_qubits[j - 1])) return fail(PSUM_ERR_INVALID, "free_qubits must ascend");
+    if (n_qubits >= 3 && j < 3 && q != j && n_free >= 3) return fail(PSUM_ERR_INVALID, "the three lowest qubits must be free");
+    P.fbit[j] = (uint8_t)q;
+    fm |= 1ull << q;
+  }
+  const GateRec* gh = (const GateRec*)gates_host;
+  for (int k = 0; k < n_gates; ++k) {
+    const bool two = gh[k].kind != 0;
+    if (gh[k].kind < 0 || gh[k].kind > 2 || gh[k].a < 0 || gh[k].a >= n_free ||
+        (two && (gh[k].b < 0 || gh[k].b >= n_free || gh[k].b == gh[k].a)))
+      return fail(PSUM_ERR_INVALID, "gate %d is malformed", k);
+  }
+  P.L = n_free;
+  P.n_nonfree = n_qubits - n_free;
+  P.ntiles = 1ull << P.n_nonfree;
+  int nj = 0;
+  for (int b = 0; b < n_qubits; ++b)
+    if (!(fm >> b & 1ull)) P.nbit[nj++] = (uint8_t)b;
+  cudaStream_t st = (cudaStream_t)stream;
+  // device copy of the gate list (per-thread scratch, grows on demand)
+  static thread_local GateRec* d_gates = nullptr;
+  static thread_local int d_cap = 0;
+  if (d_cap < n_gates) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (d_gates) cudaFree(d_gates);
+    d_cap = std::max(256, 2 * n_gates);
+    CUDA_TRY(cudaMalloc(&d_gates, sizeof(GateRec) * (size_t)d_cap));
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(st));   // the previous block may still read the scratch
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_gates, gh, sizeof(GateRec) * (size_t)n_gates, cudaMemcpyHostToDevice, st));
+  static bool attr_done = false;
+  const size_t smem = ((size_t)16 << n_free) + 8 * 128 + 8 * 9 * 64;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_gate_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)16 << 12) + 8 * 128 + 8 * 9 * 64)));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)std::min<uint64_t>(P.ntiles, (uint64_t)sms * 2);
+  k_gate_block<<<grid, kThreads, smem, st>>>((double2*)psi_dev, P, d_gates, n_gates);
+  CUDA_TRY(cudaGetLastError());
+  return PSUM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // sharding
 // ---------------------------------------------------------------------------------------------

@@ -881,6 +881,91 @@ __global__ void k_gate_cx_cz(double2* __restrict__ psi, uint64_t n_quads, int c,
     }
   }
 }
+// A block of gates whose qubits fit one tile: the tile (the 2^L amplitudes that differ only in the
+// block's free qubits) is staged in shared memory once, every gate of the block is applied there, and
+// the tile is written back -- one HBM sweep per BLOCK instead of one per gate.
+struct GateRec {      // 80 bytes
+  int32_t kind;       // 0: 2x2 unitary u on tile bit a; 1: CX (control b, target a); 2: CZ (a, b)
+  int32_t a, b;
+  int32_t pad;
+  double u[8];        // row-major {u00, u01, u10, u11} as (re, im) pairs
+};
+struct GateBlockParams {
+  int L, n_nonfree;
+  uint64_t ntiles;
+  uint8_t fbit[16];   // qubit of tile bit j (ascending; the three lowest qubits come first)
+  uint8_t nbit[64];   // positions of the non-free qubits, ascending
+};
+__global__ void __launch_bounds__(kThreads, 2)
+k_gate_block(double2* __restrict__ psi, const GateBlockParams P, const GateRec* __restrict__ gates, int ngates) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  const int L = P.L, tid = threadIdx.x;
+  const uint32_t tile_amps = 1u << L;
+  uint64_t* offT = reinterpret_cast<uint64_t*>(tile + tile_amps);   // [2][64]: tile index -> offset, 6 bits per lookup
+  uint64_t* baseT = offT + 128;                                     // [9][64]: tile id -> base
+  for (int e = tid; e < 128; e += kThreads) {
+    const int k = e >> 6, v = e & 63;
+    uint64_t o = 0;
+    for (int j = 0; j < 6 && 6 * k + j < L; ++j) o |= (uint64_t)((v >> j) & 1) << P.fbit[6 * k + j];
+    offT[e] = o;
+  }
+  const int nbt = (P.n_nonfree + 5) / 6;
+  for (int e = tid; e < nbt * 64; e += kThreads) {
+    const int k = e >> 6, v = e & 63;
+    uint64_t o = 0;
+    for (int j = 0; j < 6 && 6 * k + j < P.n_nonfree; ++j) o |= (uint64_t)((v >> j) & 1) << P.nbit[6 * k + j];
+    baseT[e] = o;
+  }
+  __syncthreads();
+  for (uint64_t tile_id = blockIdx.x; tile_id < P.ntiles; tile_id += gridDim.x) {
+    uint64_t base = 0;
+    for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
+    __syncthreads();
+    for (uint32_t e = tid; e < tile_amps; e += kThreads)
+      cp_async16(&tile[e], &psi[base | offT[e & 63u] | offT[64 + (e >> 6)]]);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int k = 0; k < ngates; ++k) {
+      const GateRec G = gates[k];
+      if (G.kind == 0) {
+        const uint32_t a = (uint32_t)G.a, lowm = (1u << a) - 1u;
+        for (uint32_t p = tid; p < tile_amps / 2; p += kThreads) {
+          const uint32_t i0 = ((p & ~lowm) << 1) | (p & lowm), i1 = i0 | (1u << a);
+          const double2 v0 = tile[i0], v1 = tile[i1];
+          double2 r0, r1;
+          r0.x = G.u[0] * v0.x - G.u[1] * v0.y + G.u[2] * v1.x - G.u[3] * v1.y;
+          r0.y = G.u[0] * v0.y + G.u[1] * v0.x + G.u[2] * v1.y + G.u[3] * v1.x;
+          r1.x = G.u[4] * v0.x - G.u[5] * v0.y + G.u[6] * v1.x - G.u[7] * v1.y;
+          r1.y = G.u[4] * v0.y + G.u[5] * v0.x + G.u[6] * v1.y + G.u[7] * v1.x;
+          tile[i0] = r0;
+          tile[i1] = r1;
+        }
+      } else {
+        const uint32_t lo = (uint32_t)(G.a < G.b ? G.a : G.b), hi = (uint32_t)(G.a < G.b ? G.b : G.a);
+        const uint32_t mlo = (1u << lo) - 1u, mhi = (1u << hi) - 1u;
+        for (uint32_t p = tid; p < tile_amps / 4; p += kThreads) {
+          uint32_t i = ((p & ~mlo) << 1) | (p & mlo);            // insert a 0 at bit lo
+          i = ((i & ~mhi) << 1) | (i & mhi);                      // insert a 0 at bit hi
+          const uint32_t i11 = i | (1u << G.a) | (1u << G.b);
+          if (G.kind == 1) {                                      // CX: swap target where control = 1
+            const uint32_t i10 = i | (1u << G.b);
+            const double2 v = tile[i10];
+            tile[i10] = tile[i11];
+            tile[i11] = v;
+          } else {                                                // CZ
+            const double2 v = tile[i11];
+            tile[i11] = make_double2(-v.x, -v.y);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (uint32_t e = tid; e < tile_amps; e += kThreads)
+      psi[base | offT[e & 63u] | offT[64 + (e >> 6)]] = tile[e];
+  }
+}
+
 __global__ void k_set_basis_state(double2* __restrict__ psi, uint64_t n_amps, uint64_t index) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps;
        i += (uint64_t)gridDim.x * blockDim.x)

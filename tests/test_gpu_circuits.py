@@ -53,6 +53,7 @@ def test_gates_match_numpy(n):
             getattr(circ, g)(float(rng.standard_normal()), int(rng.integers(n)))
     got = circ.run().cpu().numpy()
     np.testing.assert_allclose(got, _np_run(circ, []), atol=1e-13)
+    np.testing.assert_allclose(circ.run_unfused().cpu().numpy(), got, atol=1e-13)
 
 
 def test_ghz_and_ansatz_energy():
@@ -87,3 +88,33 @@ def test_vqe_h2_reaches_reference_energy():
     best = min(VQE(op, EfficientSU2(2, reps=2, entanglement='linear'), optimizer='SLSQP', seed=s).run()['optimal_value']
                for s in range(3))
     assert abs(best - (-1.85727503)) < 1e-5
+
+
+@pytest.mark.parametrize('n,ent,maxq', [(14, 'linear', 12), (15, 'full', 12), (16, 'circular', 6), (13, 'linear', 5)])
+def test_fused_blocks_equal_gate_by_gate(n, ent, maxq):
+    """Gate fusion (one sweep per block of gates whose qubits fit a shared-memory tile) against the
+    gate-by-gate path and the numpy simulator; the scheduler keeps program order wherever gates share
+    a qubit."""
+    from qiskit_aqua_b200.circuits import fuse_schedule
+    rng = np.random.default_rng(n)
+    circ = EfficientSU2(n, reps=2, entanglement=ent)
+    for _ in range(6):                                   # a few gates the ansatz family lacks
+        c, t = rng.choice(n, size=2, replace=False)
+        circ.cz(int(c), int(t)).h(int(rng.integers(n))).rx(float(rng.standard_normal()), int(rng.integers(n)))
+    theta = rng.uniform(-np.pi, np.pi, circ.num_parameters)
+    fused = circ.run(theta, max_block_qubits=maxq).cpu().numpy()
+    assert circ.last_block_count < len(circ.gates) / 3
+    np.testing.assert_allclose(fused, circ.run_unfused(theta).cpu().numpy(), atol=1e-13)
+    np.testing.assert_allclose(fused, _np_run(circ, theta), atol=1e-13)
+    blocks = fuse_schedule(n, circ._bound_gates(theta), maxq)
+    assert all(len(f) <= max(maxq, 5) and set(q for g in b for q in g[1]) <= set(f) for f, b in blocks)
+
+
+def test_fused_state_preparation_20_qubits():
+    circ = EfficientSU2(20, reps=3, entanglement='linear')
+    theta = np.random.default_rng(1).uniform(-np.pi, np.pi, circ.num_parameters)
+    a = circ.run(theta)
+    b = circ.run_unfused(theta)
+    assert circ.last_block_count <= 12
+    assert float(torch.linalg.vector_norm(a - b).item()) < 1e-12
+    assert abs(float(torch.linalg.vector_norm(a).item()) - 1.0) < 1e-12
