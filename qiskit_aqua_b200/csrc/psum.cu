@@ -277,6 +277,8 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
         dp.has_im = ph.has_im;
         dp.hi_bit = ph.hi_bit;
         dp.params.quad_idx = arena_put(base, off, ph.quad_idx, host);
+        dp.params.batch = 1;
+        dp.params.batch_stride = 0;
         // 2^RB amplitudes per thread; 2^13 tiles and "big" passes run one CTA per SM, the rest two.
         // The kernel configuration (threads << RB >= 4096) fixes the static staging capacities.
         const bool big_cfg = ph.L >= 13 || ph.caps.big;
@@ -843,21 +845,80 @@ extern "C" int psum_bra_apply(psum_handle_t h, const void* phi_dev, const void* 
   return apply_local(h, (const double2*)psi_dev, (const double2*)phi_dev, nullptr, out, (cudaStream_t)stream);
 }
 
+// Launches one pass for `nb` states stored back to back (expectation only, bra = source): the CTA
+// stages the plan of a tile once and loops over the states.  partial[b * grid + block].
+static int launch_pass_batch(psum_handle_s* h, const DevPart& D, const DevPass& dp, const double2* src, int nb,
+                             uint64_t stride, double2* part, cudaStream_t st) {
+  PassParams pp = dp.params;
+  pp.accumulate = 0;
+  pp.batch = nb;
+  pp.batch_stride = stride;
+  const bool herm = h->hermitian && h->herm_pairing && D.g == 0;
+  const int mode = kModeExpect | (dp.has_im ? kModeIm : 0) | (herm ? kModeHerm : 0);
+  const bool big_cfg = (dp.threads << dp.rb) >= 4096;
+  const size_t smem = pass_smem_bytes_c(pp.L, big_cfg, pp.quad_cap, nb);
+  cudaError_t le;
+  if (dp.rb == 4)
+    le = dp.threads == 256 ? kpass_launch_4_256(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part)
+                           : kpass_launch_4_128(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part);
+  else
+    le = dp.threads == 512 ? kpass_launch_3_512(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part)
+                           : kpass_launch_3_256(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part);
+  if (le != cudaSuccess) return fail(PSUM_ERR_CUDA, "batched k_pass launch failed: %s", cudaGetErrorString(le));
+  return PSUM_OK;
+}
+
+// <psi_b|H|psi_b> for `batch` states stored back to back (VQE max_evals_grouped, vqe.py:518; ListOp
+// fronts, matrix_op.py:199-201).  One-chunk passes are launched ONCE for up to kMaxBatch states: each
+// CTA folds the plan of a tile (and builds the quadratic-group tables) once and applies it to every
+// state; the per-state sums are reduced on the device and read back with one synchronisation per
+// group of states.
 extern "C" int psum_expect_batch(psum_handle_t h, int batch, const void* psi_dev, double* out,
                                  psum_stream_t stream) {
   if (!h || !out || batch < 0) return fail(PSUM_ERR_INVALID, "bad argument");
   if (h->world != 1) return fail(PSUM_ERR_INVALID, "handle is sharded");
   if (h->terms.empty()) return fail(PSUM_ERR_EMPTY, "Operator is empty, check the operator.");
+  if (batch > 0 && (!psi_dev || ((uintptr_t)psi_dev & 15u))) return fail(PSUM_ERR_INVALID, "bad state pointer");
   PS_TRY(upload(h));
   cudaStream_t st = (cudaStream_t)stream;
   const double2* base = (const double2*)psi_dev;
-  for (int b0 = 0; b0 < batch; b0 += 256) {          // 256 device scalars per round trip
-    const int nb = std::min(256, batch - b0);
-    for (int b = 0; b < nb; ++b) {
-      const double2* psi = base + (uint64_t)(b0 + b) * n_local_amps(h);
-      size_t pcount = 0;
-      for (const DevPart& D : h->dparts) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st));
-      k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar + b, 0);
+  const uint64_t N = n_local_amps(h);
+  size_t max_grid = 1;
+  for (const DevPart& D : h->dparts) {
+    max_grid = std::max<size_t>(max_grid, (size_t)D.grid_stream);
+    for (const DevPass& dp : D.passes) max_grid = std::max<size_t>(max_grid, (size_t)dp.grid);
+  }
+  if ((size_t)kMaxBatch * max_grid > h->partial_cap) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (h->d_partial) cudaFree(h->d_partial);
+    h->d_partial = nullptr;
+    h->partial_cap = (size_t)kMaxBatch * max_grid + 4096;
+    CUDA_TRY(cudaMalloc(&h->d_partial, h->partial_cap * sizeof(double2)));
+  }
+  for (int b0 = 0; b0 < batch; b0 += kMaxBatch) {
+    const int nb = std::min(kMaxBatch, batch - b0);
+    const double2* src0 = base + (uint64_t)b0 * N;
+    bool first = true;     // first contribution to d_scalar[0 .. nb)
+    for (const DevPart& D : h->dparts) {
+      if (D.passes.empty()) {   // streaming kernel: state by state
+        for (int b = 0; b < nb; ++b) {
+          k_stream<<<D.grid_stream, kThreads, 0, st>>>(src0 + (uint64_t)b * N, src0 + (uint64_t)b * N, nullptr, D.sgroups,
+                                                       D.nsg, D.sterms, N, 0, h->d_partial + (size_t)b * D.grid_stream);
+        }
+        k_accum_batch<<<nb, kThreads, 0, st>>>(h->d_partial, D.grid_stream, h->d_scalar, first ? 0 : 1);
+        first = false;
+        continue;
+      }
+      for (const DevPass& dp : D.passes) {
+        if (dp.params.nchunks == 1 && nb > 1) {
+          PS_TRY(launch_pass_batch(h, D, dp, src0, nb, N, h->d_partial, st));
+        } else {                  // several chunks (or a single state): one launch per state
+          for (int b = 0; b < nb; ++b)
+            PS_TRY(launch_pass_batch(h, D, dp, src0 + (uint64_t)b * N, 1, N, h->d_partial + (size_t)b * dp.grid, st));
+        }
+        k_accum_batch<<<nb, kThreads, 0, st>>>(h->d_partial, dp.grid, h->d_scalar, first ? 0 : 1);
+        first = false;
+      }
     }
     CUDA_TRY(cudaGetLastError());
     PS_TRY(fetch_scalars(h, nb, out + 2 * b0, st));

@@ -43,6 +43,10 @@ struct PassParams {
   int n_nonfree;
   int accumulate;
   int quad_cap;   // doubles of the quad-table arena behind the tile
+  int batch;      // > 1: `batch` source vectors (stride batch_stride amplitudes) share the staged plan of each
+                  // tile: the fold and the table build run once per tile, not once per state
+                  // (expectation-only launches of one-chunk passes; partial[b * gridDim.x + block])
+  uint64_t batch_stride;
   uint64_t ntiles;
   uint64_t tile_begin, tile_end;  // tile range of this launch (whole pass: 0 .. ntiles)
   uint64_t roff[16];  // byte offset (16 * amplitude index) of register amplitude r inside a tile
@@ -54,12 +58,14 @@ struct PassParams {
 // layout: [offHi 64 u64][red 16 double2][baseT 9*64 u64][group records][bundle records][patterns] at
 // compile-time offsets (big = one CTA per SM), then the tile (2^L amplitudes), then the quad arena
 constexpr int kChunkSlots = 8;   // chunk records mirrored in shared memory (read every round)
+constexpr int kMaxBatch = 32;    // states per batched launch (per-warp accumulators in shared memory)
 __host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
   return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(ChunkRec) * kChunkSlots + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
          sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
 }
-__host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap) {
-  return pass_static_bytes_c(big) + ((size_t)16 << L) + 8 * (size_t)quad_cap;
+__host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap, int batch = 1) {
+  return pass_static_bytes_c(big) + ((size_t)16 << L) + 8 * (size_t)quad_cap +
+         (batch > 1 ? (size_t)16 * 16 * kMaxBatch : 0);   // [warp][state] expectation accumulators
 }
 
 __device__ __forceinline__ double flip_sign(double v, int s) {
@@ -225,6 +231,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   PatRec* pat = reinterpret_cast<PatRec*>(bun4 + (GCAP + 1));
   double2* tile = reinterpret_cast<double2*>(pat + PCAP);
   double* qtab = reinterpret_cast<double*>(tile + tile_amps);   // tables of the chunk's quadratic groups
+  double2* wacc = reinterpret_cast<double2*>(qtab + P.quad_cap);   // [warp][kMaxBatch], batched launches only
+  const int nbatch = (!STORE && EXPECT && P.batch > 1) ? P.batch : 1;
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
   const int nW = L - 5 - RB;                                 // warp/round tile bits
   const uint32_t tile_s = smem_addr(tile), grp_s = smem_addr(grp4), bun_s = smem_addr(bun4), pat_s = smem_addr(pat),
@@ -253,6 +261,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   }
   for (int e = tid; e < 4 * (P.nchunks < kChunkSlots ? P.nchunks : kChunkSlots); e += NT)
     chk4[e] = reinterpret_cast<const uint4*>(P.chunks)[e];
+  if (nbatch > 1)
+    for (int e = tid; e < (NT / 32) * kMaxBatch; e += NT) wacc[e] = make_double2(0.0, 0.0);
   __syncthreads();
   const int nrounds = (int)(tile_amps / (NT * NA));
   const int nload = (int)(tile_amps / NT);
@@ -371,17 +381,19 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     uint64_t base = 0;
     for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
 
+   for (int bb = 0; bb < nbatch; ++bb) {
+    const double2* __restrict__ srcb = src + (uint64_t)bb * P.batch_stride;
     __syncthreads();  // previous tile fully consumed
     for (int j = 0; j < nload; ++j) {
       const int e = j * NT + tid;
       const uint64_t idx = base | offLo | offHi[e >> 7];
-      cp_async16(&tile[e], &src[idx]);
+      cp_async16(&tile[e], &srcb[idx]);
       // the old y of this tile is needed when the rounds start: pull its lines into L2 now
       // (one prefetch per 128-byte line: 8 amplitudes)
       if (STORE && P.accumulate && (tid & 7) == 0)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(y + idx));
     }
-    if (one_chunk) stage_chunk(P.chunks[0], base);  // overlaps the tile load
+    if (one_chunk && bb == 0) stage_chunk(P.chunks[0], base);  // overlaps the tile load; shared by the batch
     cp_async_wait_all();
     __syncthreads();
 
@@ -459,7 +471,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
 #pragma unroll
               for (int r = 0; r < NA; ++r) pv[r] = lds_d2(pa + 512u * (uint32_t)r);
             } else {
-              const char* pp = reinterpret_cast<const char*>(src + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
+              const char* pp = reinterpret_cast<const char*>(srcb + (i0 ^ ((uint64_t)B.z | ((uint64_t)B.w << 32))));
 #pragma unroll
               for (int r = 0; r < NA; ++r) pv[r] = __ldg(reinterpret_cast<const double2*>(pp + P.roff[r]));
             }
@@ -586,8 +598,37 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           *reinterpret_cast<double2*>(reinterpret_cast<char*>(y + i0) + P.roff[r]) = yacc[r];
       }
     }
+    if (nbatch > 1) {
+      // this state's share of the tile goes to the warp's own accumulator (fixed order: deterministic)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        eacc.x += __shfl_down_sync(0xffffffffu, eacc.x, o);
+        eacc.y += __shfl_down_sync(0xffffffffu, eacc.y, o);
+      }
+      if (lane == 0) {
+        double2 a = wacc[warp * kMaxBatch + bb];
+        a.x += eacc.x;
+        a.y += eacc.y;
+        wacc[warp * kMaxBatch + bb] = a;
+      }
+      eacc = make_double2(0.0, 0.0);
+    }
+   }
   }
   if (EXPECT) {
+    if (nbatch > 1) {
+      __syncthreads();
+      for (int bb = tid; bb < nbatch; bb += NT) {
+        double2 tot = make_double2(0.0, 0.0);
+        for (int w = 0; w < NT / 32; ++w) {
+          tot.x += wacc[w * kMaxBatch + bb].x;
+          tot.y += wacc[w * kMaxBatch + bb].y;
+        }
+        if (HERM) tot.y = 0.0;
+        partial[(size_t)bb * gridDim.x + blockIdx.x] = tot;
+      }
+      return;
+    }
     if (HERM) eacc.y = 0.0;  // exactly zero for a Hermitian operator; the paired evaluation keeps 2 Re z
     double2 tot = block_reduce(eacc, red);
     if (tid == 0) partial[blockIdx.x] = tot;
@@ -683,6 +724,26 @@ k_pauli_decompose(const double2* __restrict__ M, double2* __restrict__ Wout, int
     const double inv = 1.0 / (double)N;
     for (uint64_t z = threadIdx.x; z < N; z += blockDim.x)
       Wout[x * N + z] = make_double2(row[z].x * inv, row[z].y * inv);
+  }
+}
+
+// batched expectation: out[b] (+)= sum_i partial[b * cols + i]   (one block per state)
+__global__ void __launch_bounds__(kThreads)
+k_accum_batch(const double2* __restrict__ partial, int cols, double2* __restrict__ out, int accumulate) {
+  __shared__ double2 red[kThreads / 32];
+  const double2* row = partial + (size_t)blockIdx.x * cols;
+  double2 v = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    v.x += row[i].x;
+    v.y += row[i].y;
+  }
+  double2 tot = block_reduce(v, red);
+  if (threadIdx.x == 0) {
+    if (accumulate) {
+      tot.x += out[blockIdx.x].x;
+      tot.y += out[blockIdx.x].y;
+    }
+    out[blockIdx.x] = tot;
   }
 }
 

@@ -233,3 +233,31 @@ def test_expect_host_pipelined(n, kind):
     assert abs(eng.expect(psi) - ref) <= RTOL * max(abs(ref), 1e-3)
     got2 = eng.expect_host(host)                   # second call reuses the plan and the streams
     assert abs(got2 - got) <= 1e-13 * max(abs(got), 1e-3)
+
+
+@pytest.mark.parametrize('kind,n,opts', [('c4', 16, {}), ('c4', 16, {'reg_bits': 4}), ('c5', 15, {}), ('c5', 15, {'cta_mode': 1}),
+                                         ('molecular', 14, {}), ('small', 8, {}), ('c4', 17, {'tile_bits': 13})])
+def test_batched_expectation_shares_the_staged_plan(kind, n, opts):
+    """psum_expect_batch: one launch per pass for up to 32 states (the fold / table build of a tile is
+    shared by the batch) against the per-state expectation and the oracle; batches above 32 states and
+    passes with several chunks take the per-state launches."""
+    if kind == 'c4':
+        n, x, z, y, c = W.ising_heisenberg(n, n_triples=2500, seed=3)
+    elif kind == 'c5':
+        n, x, z, y, c = W.random_weighted_paulis(n, 2500, 4, seed=5)
+    elif kind == 'molecular':
+        n, x, z, y, c = W.molecular_style(n)
+    else:
+        n, x, z, y, c = W.two_local_random(n, 40, seed=1)
+    eng = PauliSumEngine(n, x, z, y, c, opts)
+    rng = np.random.default_rng(n)
+    for batch in (1, 5, 40):
+        psis = rng.standard_normal((batch, 1 << n)) + 1j * rng.standard_normal((batch, 1 << n))
+        psis /= np.linalg.norm(psis, axis=1)[:, None]
+        dev = torch.from_numpy(psis).cuda()
+        got = eng.expect_batch(dev)
+        one = np.array([eng.expect(dev[b]) for b in range(batch)])
+        ref = np.array([np.vdot(psis[b], co.apply(n, x, z, y, c, psis[b])) for b in range(min(batch, 3))])
+        scale = max(1.0, np.abs(one).max())
+        assert np.abs(got - one).max() <= 1e-12 * scale
+        assert np.abs(got[:len(ref)] - ref).max() <= RTOL * max(1.0, np.abs(ref).max())
