@@ -558,11 +558,28 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                   for (int e = 0; e < nent; ++e) {
                     const uint32_t ent = (uint32_t)ents & 0xffffu;
                     ents >>= 16;
-                    const double sc = pattern_sum(pat_s, p, (int)(ent & 0x7ffu), t0);
-                    switch (ent >> 11) {
-#define PSUM_CLASS_CASE(C) case C: add_class<NA, C, ND>(D, sc); break;
-                      PSUM_REP32(PSUM_CLASS_CASE)
+                    const int cnt = (int)(ent & 0x7ffu);
+                    double sc;
+                    if (cnt == 1) {   // the common case: one pattern per class entry
+                      const uint4 rec = lds_u4(pat_s + 16u * (uint32_t)p);
+                      sc = __hiloint2double((int)(rec.y ^ ((uint32_t)(__popc(rec.z & t0)) << 31)), (int)rec.x);
+                      ++p;
+                    } else {
+                      sc = pattern_sum(pat_s, p, cnt, t0);
+                    }
+                    const uint32_t zr = (ent >> 11) & (uint32_t)(NA - 1);
+                    if (IM && (ent >> 11) >= (uint32_t)NA) {
+                      switch (zr) {
+#define PSUM_CLASS_CASE(C) case C: add_class<NA, (C < NA ? NA + C : ND), ND>(D, sc); break;
+                        PSUM_REP32(PSUM_CLASS_CASE)
 #undef PSUM_CLASS_CASE
+                      }
+                    } else {
+                      switch (zr) {
+#define PSUM_CLASS_CASE(C) case C: add_class<NA, (C < NA ? C : ND), ND>(D, sc); break;
+                        PSUM_REP32(PSUM_CLASS_CASE)
+#undef PSUM_CLASS_CASE
+                      }
                     }
                   }
                   if (IM && ((h0.y >> 20) & 1u)) {
