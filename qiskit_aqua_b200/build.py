@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, 'libpsum.so')
 OBJDIR = os.path.join(CSRC, 'build')
 KPASS_CONFIGS = [(3, 256), (3, 512), (4, 128), (4, 256)]
 DEPS = ['psum.cu', 'psum_kpass_inst.cu', 'psum_kpass.h', 'psum_kernels.cuh', 'psum_plan.h', 'psum_eig.h',
-        'psum_lanczos.inc', os.path.join('..', '..', 'include', 'psum.h')]
+        'psum_lanczos.inc', 'psum_hostcopy.h', os.path.join('..', '..', 'include', 'psum.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

@@ -15,6 +15,7 @@
 
 #include "../../include/psum.h"
 #include "psum_eig.h"
+#include "psum_hostcopy.h"
 #define PSUM_SMALL_KERNELS
 #include "psum_kernels.cuh"
 #include "psum_kpass.h"
@@ -165,6 +166,7 @@ struct psum_handle_s {
   size_t bounce_bytes = 0;
   int bounce_next = 0;
   int copy_threads = 0;     // 0 = auto
+  psum::CopyPool* copy_pool = nullptr;   // persistent copy threads (created by the first pageable transfer)
   // exchange instrumentation (option "profile_exchange") and the compute-only mode used to measure
   // how much of the exchange hides behind the passes (option "skip_exchange")
   int profile_exchange = 0, skip_exchange = 0;
@@ -376,6 +378,8 @@ extern "C" int psum_destroy(psum_handle_t h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_free) cudaEventDestroy(h->ev_free);
+  delete h->copy_pool;
+  h->copy_pool = nullptr;
   for (int i = 0; i < psum_handle_s::kBounceSlots; ++i) {
     if (h->bounce_buf[i]) cudaFreeHost(h->bounce_buf[i]);
     if (h->bounce_done[i]) cudaEventDestroy(h->bounce_done[i]);
@@ -734,19 +738,9 @@ static int copy_thread_count(const psum_handle_s* h) {
   cpu_set_t set;
   int cores = 8;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
-  return std::max(2, std::min(12, cores / std::max(1, h->world)));   // ranks of one node share the cores
-}
-
-static void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
-  const size_t slice = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
-  std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; ++t) {
-    const size_t o = (size_t)t * slice;
-    if (o >= bytes) break;
-    th.emplace_back([=]() { memcpy(dst + o, src + o, std::min(slice, bytes - o)); });
-  }
-  memcpy(dst, src, std::min(slice, bytes));
-  for (auto& t : th) t.join();
+  // ranks of one node share the cores; one core stays free for the thread that feeds the GPU
+  const int share = cores / std::max(1, h->world);
+  return std::max(2, std::min(12, share > 4 ? share - 2 : share));
 }
 
 // dst_dev[0..bytes) <- src_host (pageable) through the pinned ring, DMA on stream cs
@@ -760,12 +754,16 @@ static int bounce_copy(psum_handle_s* h, const char* src, char* dst, size_t byte
     h->bounce_bytes = slot_bytes;
   }
   const int nthreads = copy_thread_count(h);
+  if (!h->copy_pool || h->copy_pool->threads() != nthreads) {
+    delete h->copy_pool;
+    h->copy_pool = new psum::CopyPool(nthreads);
+  }
   for (size_t off = 0; off < bytes; off += slot_bytes) {
     const size_t nb = std::min(slot_bytes, bytes - off);
     const int s = h->bounce_next;
     h->bounce_next = (s + 1) % psum_handle_s::kBounceSlots;
     CUDA_TRY(cudaEventSynchronize(h->bounce_done[s]));   // the DMA that last read this slot is done
-    parallel_memcpy(h->bounce_buf[s], src + off, nb, nthreads);
+    h->copy_pool->copy(h->bounce_buf[s], src + off, nb);   // streaming stores, see psum_hostcopy.h
     CUDA_TRY(cudaMemcpyAsync(dst + off, h->bounce_buf[s], nb, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaEventRecord(h->bounce_done[s], cs));
   }
