@@ -44,6 +44,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'pauli_sum_apply_throughput'
 UNIT = 'G term-amps/s'
+H2D_GBS = 55.6      # pinned H2D copy rate measured on this pool's B200 hosts (tools/h2d_probe.py, profiles/)
 NVLINK_GBS = 900.0          # NVLink 5, per direction per GPU
 SM_CLOCK_MHZ = 1965.0
 NUM_SMS = 148
@@ -65,6 +66,7 @@ def parse_args():
     ap.add_argument('--low-bits', type=int, default=0)
     ap.add_argument('--reg-bits', type=int, default=0)
     ap.add_argument('--cta-mode', type=int, default=-1)
+    ap.add_argument('--late-split', type=int, default=-1)
     ap.add_argument('--min-bundle', type=int, default=0)
     ap.add_argument('--share-weight', type=int, default=-1)
     ap.add_argument('--comm-sms', type=int, default=-1)
@@ -293,6 +295,8 @@ def main():
         eng.set_option('comm_sms', args.comm_sms)
     if args.peer_copy >= 0:
         eng.set_option('peer_copy', args.peer_copy)
+    if args.late_split >= 0:
+        eng.set_option('late_split', args.late_split)
     info = eng.info()
     gx_total = info['n_xgroups']
 
@@ -418,6 +422,12 @@ def main():
                              'host_gbs': 16.0 * N_loc * world / (ms_pin * 1e-3) / 1e9, 'energy': e_pin.real}
             e2e['pageable_over_pinned'] = ms_pg / ms_pin
             del host_pin
+        if world == 1:      # the same expectation with psi already resident: what the copy has to hide behind
+            eng.expect(psi)
+            ms_dev, _ = timed(lambda: eng.expect(psi), ksteps)
+            e2e['device_expect_ms'] = ms_dev
+            e2e['h2d_floor_ms'] = 16.0 * N_loc / (H2D_GBS * 1e9) * 1e3
+            e2e['h2d_peak_gbs'] = H2D_GBS
         if parity is not None:
             parity['rel_err_energy_e2e_vs_device'] = abs(e_pg.real - energy.real) / max(abs(energy.real), 1e-300)
 

@@ -118,6 +118,8 @@ struct DevPass {
   PassParams params;
   bool has_im = false;
   int hi_bit = 0;
+  uint64_t free_mask = 0;   // local qubits of the pass's free set
+  bool has_remote = false;  // some member reads partners from global memory (x-mask outside the free set)
   int rb = 3;
   int threads = 256;
   int grid = 0;
@@ -166,6 +168,7 @@ struct psum_handle_s {
   size_t bounce_bytes = 0;
   int bounce_next = 0;
   int copy_threads = 0;     // 0 = auto
+  int late_split = 1;       // option "late_split": host-state plan gives every late qubit passes of its own (run_ready)
   psum::CopyPool* copy_pool = nullptr;   // persistent copy threads (created by the first pageable transfer)
   // exchange instrumentation (option "profile_exchange") and the compute-only mode used to measure
   // how much of the exchange hides behind the passes (option "skip_exchange")
@@ -278,6 +281,8 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
         dp.rb = ph.rb;
         dp.has_im = ph.has_im;
         dp.hi_bit = ph.hi_bit;
+        dp.free_mask = ph.free_mask;
+        dp.has_remote = ph.n_remote > 0;
         dp.params.quad_idx = arena_put(base, off, ph.quad_idx, host);
         dp.params.batch = 1;
         dp.params.batch_stride = 0;
@@ -430,6 +435,9 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
   } else if (k == "cta_mode") {
     if (value < 0 || value > 2) return fail(PSUM_ERR_INVALID, "cta_mode must be 0 (auto), 1 (two CTAs per SM) or 2 (one big CTA)");
     h->opt.cta_mode = (int)value;
+  } else if (k == "late_split") {
+    h->late_split = h->opt.late_split = value ? 1 : 0;
+    h->parts_h.clear();   // the host-state plan is rebuilt on its next use
   } else if (k == "late_bits") {
     if (value < 0 || value > 8) return fail(PSUM_ERR_INVALID, "late_bits must be 0..8");
     h->opt.late_bits = (int)value;
@@ -779,6 +787,30 @@ struct CopyGuard {
   }
 };
 
+// Host-state pipeline: the state arrives in 2^late chunks, in index order (chunk = the top `late` local
+// qubits).  A pass whose free set holds the late qubits T combines, in one tile, the 2^|T| chunks that
+// differ in T; the tiles with given values of the OTHER late qubits form one contiguous tile range (the
+// non-free late qubits are the top bits of the tile id), complete as soon as its last chunk -- the one
+// with every bit of T set -- has landed.  After chunk k this launches every such range: chunk-local
+// passes (T = 0) run on chunk k itself, a pass that frees only late qubit t runs its range when the
+// upper chunk of the pair arrives, and only passes that free ALL late qubits (or read partners from
+// global memory) wait for the whole state.  Expectation only (no y): every launch adds its own partials.
+static int run_ready(psum_handle_s* h, const DevPart& D, const double2* psi, uint64_t k, int late, int cbits,
+                     size_t* pcount, cudaStream_t st) {
+  const uint64_t lmask = (1ull << late) - 1;
+  for (size_t pi = 0; pi < D.passes.size(); ++pi) {
+    const DevPass& dp = D.passes[pi];
+    const uint64_t T = dp.has_remote ? lmask : ((dp.free_mask >> cbits) & lmask);
+    if ((k & T) != T) continue;
+    uint64_t u = 0;
+    int j = 0;
+    for (int b = 0; b < late; ++b)
+      if (!(T >> b & 1ull)) u |= ((k >> b) & 1ull) << j++;
+    PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, pcount, st, pi, pi + 1, u, 1ull << j));
+  }
+  return PSUM_OK;
+}
+
 // <psi|H|psi> for a state that lives in HOST memory: the H2D copy is cut into 2^late_bits chunks
 // on a copy stream and every "early" pass (hi_bit inside a chunk) runs chunk by chunk as the data
 // arrives; only the passes that combine different chunks wait for the whole state.
@@ -812,8 +844,6 @@ extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi
   if (h->dparts_h.size() != 1) return fail(PSUM_ERR_INVALID, "unexpected plan shape");
   const DevPart& D = h->dparts_h[0];
   const int cbits = h->n_loc - late;
-  size_t n_early = 0;  // early passes come first in the plan (stage 1 of choose_passes)
-  while (n_early < D.passes.size() && D.passes[n_early].hi_bit < cbits) ++n_early;
   const double2* psi = (const double2*)psi_dev;
   const bool pageable = host_is_pageable(psi_host);
   size_t pcount = 0;
@@ -826,10 +856,8 @@ extern "C" int psum_expect_host(psum_handle_t h, const void* psi_host, void* psi
     else CUDA_TRY(cudaMemcpyAsync(dst, srcp, cbytes, cudaMemcpyHostToDevice, h->copy_stream));
     CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
-    if (n_early) PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, 0, n_early, k, nchunks));
+    PS_TRY(run_ready(h, D, psi, k, late, cbits, &pcount, st));
   }
-  if (n_early < D.passes.size())
-    PS_TRY(run_part(h, D, psi, psi, nullptr, 0, true, true, &pcount, st, n_early, D.passes.size()));
   k_reduce_partials<<<1, kThreads, 0, st>>>(h->d_partial, (int)pcount, h->d_scalar, 0);
   CUDA_TRY(cudaGetLastError());
   PS_TRY(fetch_scalars(h, 1, out, st));   // st waited for every chunk: the copies are complete
@@ -1327,6 +1355,7 @@ static int ensure_host_plan(psum_handle_s* h, int late) {
   if (!h->parts_h.empty() && h->late_bits_h == late) return PSUM_OK;
   PlanOptions o = h->opt;
   o.late_bits = late;
+  o.late_split = h->late_split;
   h->parts_h = build_parts(h->terms, h->n, h->p_bits, h->rank, o);
   if (h->arena_h) cudaFree(h->arena_h);
   h->arena_h = nullptr;
@@ -1340,7 +1369,7 @@ static int ensure_host_plan(psum_handle_s* h, int late) {
   const int cbits = h->n_loc - late;
   for (const DevPart& D : h->dparts_h) {
     need_h += (size_t)D.grid_stream;
-    for (const DevPass& dp : D.passes) need_h += (size_t)dp.grid * (dp.hi_bit < cbits ? nchunks : 1);
+    for (const DevPass& dp : D.passes) need_h += (size_t)dp.grid * nchunks;   // upper bound: one block per tile range
   }
   if (need_h + 4096 > h->partial_cap) {
     CUDA_TRY(cudaDeviceSynchronize());  // earlier launches may still read the old buffer
@@ -1471,8 +1500,7 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
     CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
     const size_t cbytes = (N * sizeof(double2)) >> late;
     const int cbits = h->n_loc - late;
-    if (local && late > 0)
-      while (n_early < local->passes.size() && local->passes[n_early].hi_bit < cbits) ++n_early;
+    const bool pipelined = local && late > 0 && !local->passes.empty() && !y;
     const bool pageable = host_is_pageable(host_src);
     guard.cs = h->copy_stream;
     for (uint64_t k = 0; k < nchunks; ++k) {
@@ -1482,10 +1510,9 @@ static int sharded_impl(psum_handle_s* h, const void* psi_dev, void* y_dev, void
       else CUDA_TRY(cudaMemcpyAsync(dst, srcp, cbytes, cudaMemcpyHostToDevice, h->copy_stream));
       CUDA_TRY(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
       CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[k], 0));
-      if (n_early)
-        PS_TRY(run_part(h, *local, psi, psi, nullptr, 0, true, remote.empty() && n_early == local->passes.size(),
-                        &pcount, st, 0, n_early, k, nchunks));
+      if (pipelined) PS_TRY(run_ready(h, *local, psi, k, late, cbits, &pcount, st));
     }
+    if (pipelined) n_early = local->passes.size();   // every tile range has been launched
   }
   if (any_remote) {
     CUDA_TRY(cudaEventRecord(h->ev_ready, st));   // st has waited for every chunk by now

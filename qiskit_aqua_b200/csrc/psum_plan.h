@@ -201,6 +201,8 @@ struct PlanOptions {
   int min_cover = 3;
   int plan_tries = 8;  // randomised greedy restarts of the pass planner; the cheapest plan wins
   int late_bits = 0;   // top local qubits kept out of the early passes (see choose_passes)
+  int late_split = 0;  // 1: groups that touch ONE late qubit get passes that free only that late qubit, so
+                       // their tiles complete chunk pair by chunk pair while the state arrives (run_ready)
   int reg_bits = 3;    // 3: 8 amplitudes per thread, 256-thread CTAs; 4: 16 per thread, 128-thread CTAs
   int share_weight = 100;  // percent: weight of the partner-load term when the register qubits are chosen
   int min_bundle = 2;  // a bundle of fewer members, all of them fast, is split into singles (own loads,
@@ -256,7 +258,8 @@ struct PassChoice {
 };
 
 inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks, int n_loc, int L,
-                                             int c, int min_cover, uint64_t seed = 0, int late_bits = 0) {
+                                             int c, int min_cover, uint64_t seed = 0, int late_bits = 0,
+                                             int late_split = 0) {
   std::vector<PassChoice> passes;
   uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
   auto noise = [&]() {  // seed 0 -> deterministic greedy; otherwise scores are jittered by <= 40 %
@@ -332,6 +335,17 @@ inline std::vector<PassChoice> choose_passes(const std::vector<uint64_t>& masks,
     std::vector<int> left1;
     run_stage(stage1, all & ~late, left1);
     for (int i : left1) stage2.push_back(i);
+    if (late_split) {
+      // stage 1.5: one late qubit at a time, lowest first (its chunk pairs complete earliest)
+      for (int t = n_loc - late_bits; t < n_loc; ++t) {
+        std::vector<int> mine, rest, leftt;
+        for (int i : stage2) ((masks[i] & late) == (1ull << t) ? mine : rest).push_back(i);
+        if (mine.empty()) continue;
+        run_stage(mine, (all & ~late) | (1ull << t), leftt);
+        stage2.swap(rest);
+        for (int i : leftt) stage2.push_back(i);
+      }
+    }
   } else {
     for (int i : stage1) stage2.push_back(i);
     std::sort(stage2.begin(), stage2.end());
@@ -818,7 +832,7 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
       std::vector<PassChoice> pcs;
       long best_cost = -1;
       for (int t = 0; t < std::max(1, opt.plan_tries); ++t) {
-        std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t, opt.late_bits);
+        std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t, opt.late_bits, opt.late_split);
         long n_remote = 0;
         for (auto& pc : cand)
           for (int mi : pc.members)

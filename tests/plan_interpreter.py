@@ -76,8 +76,8 @@ def _deposit(values, positions):
     return out
 
 
-def run_pass(ps, src, y=None, herm=False, check=True):
-    """Emulates one k_pass launch over all tiles.  Adds the pass's contribution to y (if given)
+def run_pass(ps, src, y=None, herm=False, check=True, tiles=None):
+    """Emulates one k_pass launch over all tiles (or the tile-id range `tiles` = (begin, end)).  Adds the pass's contribution to y (if given)
     and returns sum conj(src_i) * contribution_i (with `herm`: the paired 2 Re z evaluation of the
     Hermitian expectation kernels, imaginary part forced to zero as the kernel does)."""
     L, nnf, rb = ps['L'], ps['n_nonfree'], ps['rb']
@@ -92,7 +92,7 @@ def run_pass(ps, src, y=None, herm=False, check=True):
         regq |= 1 << int(ps['fbit'][j])
     groups, chunks, bundles = ps['groups'], ps['chunks'], ps['bundles']
     total = 0.0 + 0.0j
-    for tile_id in range(1 << nnf):
+    for tile_id in (range(1 << nnf) if tiles is None else range(*tiles)):
         base = _deposit(np.array([tile_id], dtype=np.uint64), ps['nbit'][:nnf])[0]
         idx = base | off
         idx0 = idx & ~np.uint64(regq)              # i0 | lane/warp bits, register qubits clear

@@ -53,6 +53,7 @@ CASES = [
     (12, 1500, {'tile_bits': 11}, {'x_pool': 6}),                        # many classes per group: sub-groups
     (14, 200, {'tile_bits': 11}, {'dense': 12}),                         # x-masks no pass can hold: remote groups
     (13, 600, {'tile_bits': 11, 'late_bits': 2}, {}),                    # host-state plan (early passes chunk-local)
+    (14, 600, {'tile_bits': 11, 'late_bits': 2, 'late_split': 1}, {}),   # host-state plan, one late qubit per late pass
     (13, 300, {'tile_bits': 13}, {}),
     (12, 600, {'tile_bits': 11}, {'no_y': True, 'complex_weights': False}),   # real-only passes (IM = false kernels)
     (11, 300, {'tile_bits': 11, 'reg_bits': 4}, {}),
@@ -204,3 +205,46 @@ def test_bench_workload_shapes(kind, rb):
     if eng.info()['is_hermitian']:
         e = pi.run_part(passes, psi, None, herm=True)
         assert abs(e.real - np.vdot(psi, want).real) <= 1e-11 * max(1.0, abs(np.vdot(psi, want)))
+
+
+@pytest.mark.parametrize('n,T,late,split', [(14, 500, 2, 1), (15, 700, 3, 1), (14, 500, 2, 0)])
+def test_host_pipeline_schedule_only_reads_arrived_chunks(n, T, late, split):
+    """psum_expect_host / run_ready (psum.cu): the state arrives in 2^late chunks in index order; after
+    chunk k every pass launches the tile range whose chunks are all present.  Emulated here with the
+    exported plan: amplitudes that have not arrived are NaN, so a range launched too early poisons the
+    sum; every tile must be launched exactly once and the total must equal <psi|H|psi>."""
+    rng = np.random.default_rng(31 * n + T + late)
+    x, z, ypow, c = random_terms(n, T, rng, complex_weights=False)
+    eng = PauliSumEngine(n, x, z, ypow, c, options={'tile_bits': 11, 'late_bits': late, 'late_split': split})
+    passes = pi.export_part(eng, 0)
+    cbits = n - late
+    lmask = (1 << late) - 1
+    psi = random_state(n, rng)
+    arrived = np.full(1 << n, np.nan + 0j)
+    total = 0.0 + 0.0j
+    launched = [0] * len(passes)
+    n_progressive = 0
+    for k in range(1 << late):
+        arrived[k << cbits:(k + 1) << cbits] = psi[k << cbits:(k + 1) << cbits]
+        for p, ps in enumerate(passes):
+            free = 0
+            for j in range(ps['L']):
+                free |= 1 << int(ps['fbit'][j])
+            T_ = lmask if eng.pass_info(p)['n_remote_groups'] else (free >> cbits) & lmask
+            if (k & T_) != T_:
+                continue
+            u, j = 0, 0
+            for b in range(late):
+                if not (T_ >> b) & 1:
+                    u |= ((k >> b) & 1) << j
+                    j += 1
+            per = (1 << ps['n_nonfree']) >> j
+            total += pi.run_pass(ps, arrived, None, tiles=(u * per, (u + 1) * per))
+            launched[p] += per
+            if T_ and k != lmask:
+                n_progressive += 1
+    assert launched == [1 << ps['n_nonfree'] for ps in passes]
+    want = np.vdot(psi, po.mf_apply(n, x, z, ypow, c, psi))
+    assert np.isfinite(total.real) and abs(total - want) <= 1e-11 * max(1.0, abs(want))
+    if split:
+        assert n_progressive > 0        # some late ranges ran before the last chunk arrived
