@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument('--reg-bits', type=int, default=0)
     ap.add_argument('--cta-mode', type=int, default=-1)
     ap.add_argument('--late-split', type=int, default=-1)
+    ap.add_argument('--host-chunk-bits', type=int, default=0)
+    ap.add_argument('--copy-threads', type=int, default=0)
     ap.add_argument('--min-bundle', type=int, default=0)
     ap.add_argument('--share-weight', type=int, default=-1)
     ap.add_argument('--comm-sms', type=int, default=-1)
@@ -297,6 +299,10 @@ def main():
         eng.set_option('peer_copy', args.peer_copy)
     if args.late_split >= 0:
         eng.set_option('late_split', args.late_split)
+    if args.host_chunk_bits:
+        eng.set_option('host_chunk_bits', args.host_chunk_bits)
+    if args.copy_threads:
+        eng.set_option('copy_threads', args.copy_threads)
     info = eng.info()
     gx_total = info['n_xgroups']
 
