@@ -150,6 +150,16 @@ int psum_lanczos(psum_handle_t h, int k, double tol, int max_iter, uint64_t seed
                  int64_t mem_budget_bytes, double* evals, void* evecs_dev, double* resid_out,
                  int* iters_out, psum_stream_t stream);
 
+/* The same entry point for NON-Hermitian sums (complex label coefficients), which the reference's
+ * eigs(which='SR') -- ARPACK's Arnoldi -- accepts at numpy_eigen_solver.py:175-176: Krylov-Schur
+ * Arnoldi on the device matvec (sharded like psum_lanczos).  evals_re_im: 2k doubles (re, im
+ * interleaved), ascending by (real, imaginary) part like the reference's eigval.argsort() (:177-180).
+ * evecs_dev: k*N_loc complex128 unit-norm right eigenvectors or NULL; resid_out: k norms
+ * |H v - lambda v| or NULL.  Works for Hermitian sums too (then it equals psum_lanczos). */
+int psum_arnoldi(psum_handle_t h, int k, double tol, int max_iter, uint64_t seed,
+                 int64_t mem_budget_bytes, double* evals_re_im, void* evecs_dev, double* resid_out,
+                 int* iters_out, psum_stream_t stream);
+
 /* ---- time evolution on the matvec: out = exp(-i t H) psi ("next" row of SURVEY 8f) ----------
  * Replaces the exact branch of MatrixOperator.evolve (legacy/matrix_operator.py:354-355) and
  * MatrixEvolution (evolutions/matrix_evolution.py:32-63) with Krylov (Lanczos) exponentiation:
@@ -224,6 +234,12 @@ int psum_exchange_stats(psum_handle_t h, double out[4]);
 /* Host-side eigen-solver test hook (no device): which = 0 dense Jacobi (A = n*n), 1 tridiagonal
  * QL (A = d[n], e[n]).  w[n] ascending, V n*n eigenvectors in columns (may be NULL). */
 int psum_test_eigh(int which, int n, const double* A, double* w, double* V);
+/* Host-side test hooks of the Arnoldi path (no device): complex Schur form A = Z T Z^H of a dense n x n
+ * matrix (row-major, re/im interleaved) with the diagonal ordered by (real, imaginary) part; and the
+ * Krylov-Schur driver of psum_arnoldi run on a dense matrix with host vectors (m = basis size, 0 auto). */
+int psum_test_schur(int n, const double* A_re_im, double* T_re_im, double* Z_re_im);
+int psum_test_arnoldi(int n, const double* A_re_im, int k, int m, double tol, int max_iter, uint64_t seed,
+                      double* evals_re_im, double* evecs_re_im, double* resid_out, int* iters_out);
 int psum_allreduce_sum(psum_handle_t h, double* host_vals, int n); /* small host scalars */
 
 #ifdef __cplusplus

@@ -38,6 +38,8 @@ SIGNATURES = {
     'psum_diag_kmin': (C.c_int, [_vp, C.c_int, _dp, _u64p, _vp]),
     'psum_lanczos': (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int64, _dp, _vp,
                                _dp, C.POINTER(C.c_int), _vp]),
+    'psum_arnoldi': (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_int64, _dp, _vp,
+                               _dp, C.POINTER(C.c_int), _vp]),
     'psum_evolve': (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int),
                               C.POINTER(C.c_int), _vp]),
     'psum_state_basis': (C.c_int, [_vp, C.c_int, C.c_uint64, _vp]),
@@ -56,6 +58,9 @@ SIGNATURES = {
     'psum_expect_sharded_host': (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, _dp, _vp]),
     'psum_allreduce_sum': (C.c_int, [_vp, _dp, C.c_int]),
     'psum_test_eigh': (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp]),
+    'psum_test_schur': (C.c_int, [C.c_int, _dp, _dp, _dp]),
+    'psum_test_arnoldi': (C.c_int, [C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, _dp, _dp, _dp,
+                                    C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -113,11 +113,12 @@ class NumPyEigensolver:
             self._k = min(self._in_k, 2 ** self._operator.num_qubits)
 
     # -- solve --------------------------------------------------------------------------------------
-    # dense branch (k >= 2^n - 1, or more pairs than the Lanczos basis holds, or a non-Hermitian sum):
+    # dense branch (k >= 2^n - 1, or more pairs than the Krylov basis holds, or a tiny non-Hermitian sum):
     # the matrix is written on the device and diagonalised there by the dense library routine, as the
     # reference does with np.linalg.eig (:171-173).  Bounded by the size of the dense matrix.
     DENSE_MAX_QUBITS = 13
     LANCZOS_MAX_K = 120
+    ARNOLDI_MIN_QUBITS = 7      # non-Hermitian sums above this size: device Arnoldi instead of the dense matrix
 
     def _solve_dense(self, eng, n, k_keep):
         if n > self.DENSE_MAX_QUBITS:
@@ -174,13 +175,19 @@ class NumPyEigensolver:
         # eigenpairs (not truncated to k); aux operators are still evaluated for the first k only
         if self._k >= N - 1:
             return self._solve_dense(eng, n, N)
+        if not info['is_hermitian'] and n > self.ARNOLDI_MIN_QUBITS and self._k <= self.LANCZOS_MAX_K:
+            # eigs(which='SR') accepts complex weights (ARPACK's Arnoldi): Krylov-Schur Arnoldi on the
+            # device matvec; eigenvalues ascending by (real, imaginary) part like eigval.argsort() (:177-180)
+            r = eng.arnoldi(k=self._k, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
+            self._ret['eigvals'] = r['evals']
+            self._ret['eigvecs'] = r['evecs']
+            return
         if not info['is_hermitian'] or self._k > self.LANCZOS_MAX_K:
-            # eigs(which='SR') accepts complex weights (Arnoldi); on the device only the dense routine does
+            # tiny non-Hermitian sums, or more pairs than a Krylov basis holds: the dense routine
             if n > self.DENSE_MAX_QUBITS:
-                why = 'a non-Hermitian Pauli sum (complex label coefficients)' if not info['is_hermitian'] \
-                    else 'k = %d > %d' % (self._k, self.LANCZOS_MAX_K)
-                raise AquaError('NumPyEigensolver on the GPU: %s needs the dense branch, limited to %d qubits; '
-                                'no CPU fallback is provided' % (why, self.DENSE_MAX_QUBITS))
+                raise AquaError('NumPyEigensolver on the GPU: k = %d > %d needs the dense branch, limited to %d '
+                                'qubits; no CPU fallback is provided' % (self._k, self.LANCZOS_MAX_K,
+                                                                         self.DENSE_MAX_QUBITS))
             return self._solve_dense(eng, n, self._k)
         r = eng.lanczos(k=self._k, tol=self._tol, max_iter=self._max_iter, seed=self._seed)
         self._ret['eigvals'] = r['evals'].astype(np.complex128)      # eigs returns complex values

@@ -255,6 +255,26 @@ class PauliSumEngine:
         return {'evals': np.array(ev[:]), 'evecs': vecs,
                 'resid': np.array(rs[:]) if want_residuals else None, 'iters': it.value}
 
+    def arnoldi(self, k=1, tol=1e-12, max_iter=3000, seed=1, mem_budget_bytes=0,
+                want_vectors=True, want_residuals=False):
+        """k eigenpairs of smallest real part of a general (non-Hermitian) Pauli sum -- eigs(which='SR') at
+        numpy_eigen_solver.py:175-176 for complex label coefficients.  Returns dict(evals complex128[k]
+        ascending by (re, im), evecs [k, N_loc] CUDA tensor, resid, iters)."""
+        if not torch.cuda.is_available():
+            raise PsumError(_lib.ERR_CUDA, 'no CUDA device available')
+        ev = (C.c_double * (2 * k))()
+        rs = (C.c_double * k)()
+        it = C.c_int(0)
+        vecs = torch.empty((k, self.n_local_amps), dtype=torch.complex128, device='cuda') \
+            if want_vectors else None
+        check(lib().psum_arnoldi(self._h, k, float(tol), int(max_iter), int(seed),
+                                 int(mem_budget_bytes), ev,
+                                 C.c_void_p(vecs.data_ptr()) if want_vectors else None,
+                                 rs if want_residuals else None, C.byref(it), _stream_ptr()))
+        e = np.array(ev[:])
+        return {'evals': e[0::2] + 1j * e[1::2], 'evecs': vecs,
+                'resid': np.array(rs[:]) if want_residuals else None, 'iters': it.value}
+
     # -- time evolution ------------------------------------------------------------------------------
     def evolve(self, psi, t, tol=1e-10, krylov_dim=0, out=None):
         """exp(-i t H) psi on the device (legacy/matrix_operator.py:354-355 without the matrix).

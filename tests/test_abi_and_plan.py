@@ -128,6 +128,51 @@ def test_host_eigensolvers():
         np.testing.assert_allclose(T @ V, V * w, atol=1e-11 * n)
 
 
+def test_host_schur_and_arnoldi_driver():
+    """The host half of psum_arnoldi: complex Schur form (sorted by real part) and the Krylov-Schur
+    restart logic, run on dense matrices with host vectors (psum_test_schur / psum_test_arnoldi)."""
+    lib = _lib.lib()
+    rng = np.random.default_rng(5)
+    dp = C.POINTER(C.c_double)
+    for n in (1, 2, 5, 33, 128):
+        for kind in range(3):
+            A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+            if kind == 1:
+                A = A + A.conj().T
+            if kind == 2:      # triangular with repeated integer eigenvalues
+                A = np.triu(A)
+                A[np.diag_indices(n)] = np.round(A.diagonal().real)
+            A = np.ascontiguousarray(A)
+            T, Z = np.zeros_like(A), np.zeros_like(A)
+            assert lib.psum_test_schur(n, A.ctypes.data_as(dp), T.ctypes.data_as(dp), Z.ctypes.data_as(dp)) == 0
+            tol = 1e-12 * max(1.0, np.abs(A).max() * n)
+            np.testing.assert_allclose(Z @ T @ Z.conj().T, A, atol=tol)
+            np.testing.assert_allclose(Z.conj().T @ Z, np.eye(n), atol=1e-12)
+            assert np.abs(np.tril(T, -1)).max() == 0.0
+            d = T.diagonal()
+            assert all((d[i].real, d[i].imag) <= (d[i + 1].real, d[i + 1].imag) for i in range(n - 1))
+            np.testing.assert_allclose(np.sort_complex(d), np.sort_complex(np.linalg.eigvals(A)), atol=100 * tol)
+    for n, k, m in ((6, 2, 0), (30, 3, 0), (200, 4, 0), (300, 6, 20), (300, 1, 12)):
+        for kind in range(3):
+            A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+            if kind == 1:
+                A = (A + A.conj().T) / 2
+            if kind == 2:      # Hermitian plus a small anti-Hermitian part
+                A = (A + A.conj().T) / 2 + 0.05 * (A - A.conj().T)
+            A = np.ascontiguousarray(A)
+            ev, vec, rs, it = np.zeros(2 * k), np.zeros((k, n), dtype=np.complex128), np.zeros(k), C.c_int(0)
+            rc = lib.psum_test_arnoldi(n, A.ctypes.data_as(dp), k, m, 1e-12, 5000, 1, ev.ctypes.data_as(dp),
+                                       vec.ctypes.data_as(dp), rs.ctypes.data_as(dp), C.byref(it))
+            assert rc == 0, _lib.last_error() if hasattr(_lib, 'last_error') else rc
+            ev = ev[0::2] + 1j * ev[1::2]
+            ref = np.linalg.eigvals(A)
+            ref = ref[np.lexsort((ref.imag, ref.real))][:k]
+            np.testing.assert_allclose(ev, ref, atol=1e-8)
+            for i in range(k):
+                assert np.linalg.norm(A @ vec[i] - ev[i] * vec[i]) < 1e-8
+                assert abs(np.linalg.norm(vec[i]) - 1.0) < 1e-10
+
+
 def test_c_oracle_matches_numpy_oracle():
     from oracle import c_oracle as co
     n, x, z, y, c = W.random_dense_paulis(13, 80, seed=11, complex_coeffs=True)

@@ -149,9 +149,9 @@ def test_lanczos_rejects_k_beyond_its_basis():
 
 
 def test_non_hermitian_sum_small_uses_dense_eig():
-    """Complex weights: the reference's eigs(which='SR') is an Arnoldi method and accepts them; on the
-    device the dense branch does (up to 13 qubits), larger ones raise."""
-    from qiskit_aqua_b200 import AquaError, NumPyEigensolver, WeightedPauliOperator, Pauli, workloads as W
+    """Complex weights: the reference's eigs(which='SR') is an Arnoldi method and accepts them; tiny sums
+    take the dense branch on the device, larger ones the device Arnoldi (psum_arnoldi)."""
+    from qiskit_aqua_b200 import NumPyEigensolver, WeightedPauliOperator, Pauli, workloads as W
     n, x, z, y, c = W.random_dense_paulis(5, 40, seed=11, complex_coeffs=True)
     op = WeightedPauliOperator(paulis=[[cc, Pauli.from_masks(int(xx), int(zz), n)] for xx, zz, cc in zip(x, z, c)])
     dense = po.ref_to_spmatrix([(complex(cc), po.masks_to_label(int(xx), int(zz), n)) for xx, zz, cc in zip(x, z, c)]).toarray()
@@ -160,10 +160,50 @@ def test_non_hermitian_sum_small_uses_dense_eig():
     ref = ref[np.argsort(ref)]
     res = NumPyEigensolver(op, k=4).run()
     np.testing.assert_allclose(res.eigenvalues, ref[:4], atol=1e-9)
+    # 15 qubits: beyond the dense branch -> Krylov-Schur Arnoldi on the matvec; checked by explicit residuals
     n2, x, z, y, c = W.random_dense_paulis(15, 30, seed=12, complex_coeffs=True)
     big = WeightedPauliOperator(paulis=[[cc, Pauli.from_masks(int(xx), int(zz), n2)] for xx, zz, cc in zip(x, z, c)])
-    with pytest.raises(AquaError):
-        NumPyEigensolver(big, k=2).run()
+    solver = NumPyEigensolver(big, k=2)
+    res = solver.run()
+    ev = np.asarray(res.eigenvalues)
+    assert ev.dtype == np.complex128 and ev[0].real <= ev[1].real
+    eng = big._engine_for()
+    scale = np.abs(c).sum()
+    for i in range(2):
+        v = solver._ret['eigvecs'][i]
+        assert abs(torch.linalg.norm(v).item() - 1.0) < 1e-10
+        assert torch.linalg.norm(eng.apply(v) - complex(ev[i]) * v).item() < 1e-8 * scale
+
+
+@pytest.mark.parametrize('n,k,T', [(8, 3, 40), (10, 4, 60), (11, 1, 25)])
+def test_arnoldi_vs_dense_eig(n, k, T):
+    """psum_arnoldi == the k eigenvalues of smallest real part of the dense matrix (what
+    eigs(which='SR') + argsort returns, numpy_eigen_solver.py:175-180), non-Hermitian sums."""
+    _, x, z, y, c = W.random_dense_paulis(n, T, seed=100 + n, complex_coeffs=True)
+    eng = PauliSumEngine(n, x, z, y, c)
+    assert not eng.info()['is_hermitian']
+    N = 1 << n
+    H = np.stack([co.apply(n, x, z, y, c, np.eye(N, dtype=complex)[j]) for j in range(N)], axis=1)
+    ref = np.linalg.eigvals(H)
+    ref = ref[np.lexsort((ref.imag, ref.real))]
+    r = eng.arnoldi(k=k, tol=1e-12, want_residuals=True)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(r['evals'], ref[:k], rtol=0, atol=1e-9 * scale)
+    assert r['resid'].max() < 1e-8 * scale
+    vecs = r['evecs'].cpu().numpy()
+    for i in range(k):
+        assert np.linalg.norm(H @ vecs[i] - r['evals'][i] * vecs[i]) < 1e-8 * scale
+
+
+def test_arnoldi_equals_lanczos_on_a_hermitian_sum():
+    n = 12
+    _, x, z, y, c = W.two_local_random(n, 150, seed=8)
+    eng = PauliSumEngine(n, x, z, y, c)
+    a = eng.arnoldi(k=3, tol=1e-12, want_residuals=True)
+    l = eng.lanczos(k=3, tol=1e-12)
+    np.testing.assert_allclose(a['evals'].real, l['evals'], rtol=0, atol=1e-9 * np.abs(l['evals']).max())
+    assert np.abs(a['evals'].imag).max() < 1e-9
+    assert a['resid'].max() < 1e-7
 
 
 def test_diagonal_operator_with_filter_uses_one_device_sort():
