@@ -57,10 +57,11 @@ struct PassParams {
 // shared memory of one k_pass CTA (bytes), L tile bits
 // layout: [offHi 64 u64][red 16 double2][baseT 9*64 u64][group records][bundle records][patterns] at
 // compile-time offsets (big = one CTA per SM), then the tile (2^L amplitudes), then the quad arena
-constexpr int kChunkSlots = 8;   // chunk records mirrored in shared memory (read every round)
+constexpr int kChunkSlots = 8;   // chunk records mirrored in shared memory (read every round); one more slot is
+                                 // refilled on the fly for the chunks of a pass beyond the first kChunkSlots
 constexpr int kMaxBatch = 32;    // states per batched launch (per-warp accumulators in shared memory)
 __host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
-  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(ChunkRec) * kChunkSlots + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
+  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(ChunkRec) * (kChunkSlots + 1) + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
          sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
 }
 __host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap, int batch = 1) {
@@ -226,7 +227,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   double2* red = reinterpret_cast<double2*>(offHi + 64);
   uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
   uint4* chk4 = reinterpret_cast<uint4*>(baseT + 9 * 64);   // the first kChunkSlots chunk records (4 x uint4 each)
-  uint4* grp4 = chk4 + 4 * kChunkSlots;                     // 3 x uint4 per group record
+  uint4* grp4 = chk4 + 4 * (kChunkSlots + 1);               // 3 x uint4 per group record
   uint4* bun4 = grp4 + 3 * (GCAP + 1);                      // 1 x uint4 per bundle record
   PatRec* pat = reinterpret_cast<PatRec*>(bun4 + (GCAP + 1));
   double2* tile = reinterpret_cast<double2*>(pat + PCAP);
@@ -313,8 +314,9 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         }
       }
       double v = 0.0;
+#pragma unroll 4
       for (uint32_t t = ta; t < tb; ++t)
-        v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+        v += flip_sign(__ldg(P.term_val + t), __popcll(base & __ldg(P.term_zb + t)) & 1);
       put_pattern(p, gp, v);
     }
     if (has_long) {
@@ -337,8 +339,9 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       // every table index; a task runs on one warp, lane = table index, so the pattern loop is uniform.
       __syncthreads();
       const int nlt = 1 + nW + RB, ntab = nlt + 1 + RB + 1;
+      const uint32_t ntab_inv = 65536u / (uint32_t)ntab + 1u;   // task / ntab by a multiplication (task < 2^12)
       for (int task = warp; task < (int)ch.nq * ntab; task += NT / 32) {
-        const int qi = task / ntab, tb = task - qi * ntab;
+        const int qi = (int)(((uint32_t)task * ntab_inv) >> 16), tb = task - qi * ntab;
         const int g = (int)P.quad_idx[(ch.q0 & 0x7fffffffu) + qi];
         const uint32_t meta = reinterpret_cast<const uint32_t*>(grp4 + 3 * g)[1];
         const uint8_t* area = reinterpret_cast<const uint8_t*>(grp4 + 3 * g) + 8;
@@ -367,6 +370,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         }
         double v = 0.0;
         const int pa = pfirst + (int)area[seg], pb = pfirst + (int)area[seg + 1];
+#pragma unroll 4
         for (int p = pa; p < pb; ++p) {
           const uint4 rec = pat4[p];
           const double c = __hiloint2double((int)(rec.y ^ ((uint32_t)__popc(rec.z & M) << 31)), (int)rec.x);
@@ -408,16 +412,24 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
                                           : make_double2(0.0, 0.0);
 
       for (int c = 0; c < P.nchunks; ++c) {
+        // the chunk record always comes from shared memory (a global fallback inside this loop is
+        // hoisted by the compiler and costs every round a long-scoreboard stall): chunks beyond the
+        // mirrored ones go through the spare slot, refilled behind the barrier that staging needs anyway
+        const int slot = c < kChunkSlots ? c : kChunkSlots;
+        if (!one_chunk) {
+          __syncthreads();  // everyone is done with the previous chunk's pat / grp (and the spare slot)
+          if (c >= kChunkSlots) {
+            if (tid < 4) chk4[4 * kChunkSlots + tid] = reinterpret_cast<const uint4*>(P.chunks + c)[tid];
+            __syncthreads();
+          }
+        }
         ChunkRec ch;
-        if (c < kChunkSlots) {
+        {
           uint4* cw = reinterpret_cast<uint4*>(&ch);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 64u * (uint32_t)c + 16u * q);
-        } else {
-          ch = P.chunks[c];
+          for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 64u * (uint32_t)slot + 16u * q);
         }
         if (!one_chunk) {
-          __syncthreads();  // everyone is done with the previous chunk's pat / grp
           stage_chunk(ch, base);
           __syncthreads();
         }

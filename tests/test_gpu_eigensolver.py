@@ -167,7 +167,7 @@ def test_non_hermitian_sum_small_uses_dense_eig():
     res = solver.run()
     ev = np.asarray(res.eigenvalues)
     assert ev.dtype == np.complex128 and ev[0].real <= ev[1].real
-    eng = big._engine_for()
+    eng = big.engine
     scale = np.abs(c).sum()
     for i in range(2):
         v = solver._ret['eigvecs'][i]
