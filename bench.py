@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument('--host-chunk-bits', type=int, default=0)
     ap.add_argument('--copy-threads', type=int, default=0)
     ap.add_argument('--min-bundle', type=int, default=0)
+    ap.add_argument('--plan-tries', type=int, default=0)
+    ap.add_argument('--min-cover', type=int, default=0)
     ap.add_argument('--share-weight', type=int, default=-1)
     ap.add_argument('--comm-sms', type=int, default=-1)
     ap.add_argument('--peer-copy', type=int, default=-1)
@@ -285,6 +287,10 @@ def main():
         opts['cta_mode'] = args.cta_mode
     if args.min_bundle:
         opts['min_bundle'] = args.min_bundle
+    if args.plan_tries:
+        opts['plan_tries'] = args.plan_tries
+    if args.min_cover:
+        opts['min_cover'] = args.min_cover
     if args.share_weight >= 0:
         opts['share_weight'] = args.share_weight
     eng = PauliSumEngine(n_total, x, z, y, c, opts)

@@ -274,13 +274,17 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   // Stage a chunk: copy its bundle and group records to shared memory, then fold -- bits outside
   // the free set become a per-tile sign of each term; equal in-tile patterns of a group are summed
   // into one coefficient, stored in pat[] and (first two patterns of a group) inline in its record.
-  auto stage_chunk = [&](const ChunkRec ch, uint64_t base) {
-    for (int g = tid; g < ch.ng * 3; g += NT)
-      grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
-    for (int b = tid; b < ch.nb; b += NT)
-      bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch.b0)[b];
-    if (tid < 3) grp4[ch.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
-    if (tid == 3) bun4[ch.nb] = make_uint4(0u, 0u, 0u, 0u);
+  // copy_records = false: the records of this chunk are already in shared memory (a one-chunk pass copies
+  // them once per CTA; every tile's fold overwrites all the coefficient slots it uses)
+  auto stage_chunk = [&](const ChunkRec ch, uint64_t base, bool copy_records) {
+    if (copy_records) {
+      for (int g = tid; g < ch.ng * 3; g += NT)
+        grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch.g0)[g];
+      for (int b = tid; b < ch.nb; b += NT)
+        bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch.b0)[b];
+      if (tid < 3) grp4[ch.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
+      if (tid == 3) bun4[ch.nb] = make_uint4(0u, 0u, 0u, 0u);
+    }
     // long term lists (a pattern that collects, e.g., every Z_a Z_b with both qubits outside the
     // tile) are deferred to a queue and folded by a whole warp each: one lane looping over a hundred
     // terms would stall its warp -- and with it the CTA -- at the next barrier
@@ -288,8 +292,8 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     uint16_t* lq = reinterpret_cast<uint16_t*>(red) + 8;
     constexpr int kLongCap = 120;
     const bool has_long = (ch.q0 >> 31) != 0;
-    if (tid == 4) *lq_count = 0;
-    __syncthreads();
+    if (has_long && tid == 4) *lq_count = 0;
+    if (copy_records || has_long) __syncthreads();
     auto put_pattern = [&](int p, int gp, double v) {
       const uint32_t zraw = P.pat_zt[gp];
       if (HERM && (zraw & 0x8000u)) v += v;
@@ -381,6 +385,21 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     }
   };
 
+  // one-chunk pass: its group / bundle records are the same for every tile -- copied once
+  if (one_chunk) {
+    ChunkRec ch0;
+    uint4* cw = reinterpret_cast<uint4*>(&ch0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 16u * q);
+    for (int g = tid; g < ch0.ng * 3; g += NT)
+      grp4[g] = reinterpret_cast<const uint4*>(P.groups + ch0.g0)[g];
+    for (int b = tid; b < ch0.nb; b += NT)
+      bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch0.b0)[b];
+    if (tid < 3) grp4[ch0.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
+    if (tid == 3) bun4[ch0.nb] = make_uint4(0u, 0u, 0u, 0u);
+    // (made visible by the barrier at the top of the first tile)
+  }
+
   for (uint64_t tile_id = P.tile_begin + blockIdx.x; tile_id < P.tile_end; tile_id += gridDim.x) {
     uint64_t base = 0;
     for (int k = 0; k < nbt; ++k) base |= baseT[k * 64 + (int)((tile_id >> (6 * k)) & 63ull)];
@@ -397,7 +416,13 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       if (STORE && P.accumulate && (tid & 7) == 0)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(y + idx));
     }
-    if (one_chunk && bb == 0) stage_chunk(P.chunks[0], base);  // overlaps the tile load; shared by the batch
+    if (one_chunk && bb == 0) {   // the fold overlaps the tile load; shared by the batch
+      ChunkRec ch0;
+      uint4* cw = reinterpret_cast<uint4*>(&ch0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 16u * q);
+      stage_chunk(ch0, base, false);
+    }
     cp_async_wait_all();
     __syncthreads();
 
@@ -430,7 +455,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
           for (int q = 0; q < 4; ++q) cw[q] = lds_u4(chk_s + 64u * (uint32_t)slot + 16u * q);
         }
         if (!one_chunk) {
-          stage_chunk(ch, base);
+          stage_chunk(ch, base, true);
           __syncthreads();
         }
         // ---- singles: a fast group alone in its bundle; one straight-line loop per (im, xr) with
