@@ -661,13 +661,7 @@ static int run_part(psum_handle_s* h, const DevPart& D, const double2* src, cons
       const bool herm = !y && h->hermitian && h->herm_pairing && bra_is_src && D.g == 0;
       const int mode = (y ? kModeStore : 0) | (ex ? kModeExpect : 0) | (dp.has_im ? kModeIm : 0) |
                        ((herm && ex) ? kModeHerm : 0);
-      cudaError_t le;
-      if (dp.rb == 4)
-        le = dp.threads == 256 ? kpass_launch_4_256(mode, grid, dp.smem, st, src, b, y, pp, part)
-                               : kpass_launch_4_128(mode, grid, dp.smem, st, src, b, y, pp, part);
-      else
-        le = dp.threads == 512 ? kpass_launch_3_512(mode, grid, dp.smem, st, src, b, y, pp, part)
-                               : kpass_launch_3_256(mode, grid, dp.smem, st, src, b, y, pp, part);
+      const cudaError_t le = kpass_launch(dp.rb, dp.threads, mode, grid, dp.smem, st, src, b, y, pp, part);
       if (le != cudaSuccess)
         return fail(PSUM_ERR_CUDA, "k_pass launch (mode %d, rb %d, %d threads) failed: %s", mode, dp.rb, dp.threads,
                     cudaGetErrorString(le));
@@ -890,13 +884,7 @@ static int launch_pass_batch(psum_handle_s* h, const DevPart& D, const DevPass& 
   const int mode = kModeExpect | (dp.has_im ? kModeIm : 0) | (herm ? kModeHerm : 0);
   const bool big_cfg = (dp.threads << dp.rb) >= 4096;
   const size_t smem = pass_smem_bytes_c(pp.L, big_cfg, pp.quad_cap, nb);
-  cudaError_t le;
-  if (dp.rb == 4)
-    le = dp.threads == 256 ? kpass_launch_4_256(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part)
-                           : kpass_launch_4_128(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part);
-  else
-    le = dp.threads == 512 ? kpass_launch_3_512(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part)
-                           : kpass_launch_3_256(mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part);
+  const cudaError_t le = kpass_launch(dp.rb, dp.threads, mode, dp.grid, smem, st, src, nullptr, nullptr, pp, part);
   if (le != cudaSuccess) return fail(PSUM_ERR_CUDA, "batched k_pass launch failed: %s", cudaGetErrorString(le));
   return PSUM_OK;
 }

@@ -55,18 +55,18 @@ struct PassParams {
 };
 
 // shared memory of one k_pass CTA (bytes), L tile bits
-// layout: [offHi 64 u64][red 16 double2][baseT 9*64 u64][group records][bundle records][patterns] at
+// layout: [offHi 64 u64][red 32 double2][baseT 9*64 u64][group records][bundle records][patterns] at
 // compile-time offsets (big = one CTA per SM), then the tile (2^L amplitudes), then the quad arena
 constexpr int kChunkSlots = 8;   // chunk records mirrored in shared memory (read every round); one more slot is
                                  // refilled on the fly for the chunks of a pass beyond the first kChunkSlots
 constexpr int kMaxBatch = 32;    // states per batched launch (per-warp accumulators in shared memory)
 __host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
-  return 8 * 64 + 16 * 16 + 8 * 9 * 64 + sizeof(ChunkRec) * (kChunkSlots + 1) + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
+  return 8 * 64 + 16 * 32 + 8 * 9 * 64 + sizeof(ChunkRec) * (kChunkSlots + 1) + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
          sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
 }
 __host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap, int batch = 1) {
   return pass_static_bytes_c(big) + ((size_t)16 << L) + 8 * (size_t)quad_cap +
-         (batch > 1 ? (size_t)16 * 16 * kMaxBatch : 0);   // [warp][state] expectation accumulators
+         (batch > 1 ? (size_t)16 * 32 * kMaxBatch : 0);   // [warp][state] expectation accumulators (<= 32 warps)
 }
 
 __device__ __forceinline__ double flip_sign(double v, int s) {
@@ -225,7 +225,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   constexpr int PCAP = BIG ? kPatCapBig : kPatCapSmall, GCAP = BIG ? kGrpCapBig : kGrpCapSmall;
   uint64_t* offHi = reinterpret_cast<uint64_t*>(smem_raw);
   double2* red = reinterpret_cast<double2*>(offHi + 64);
-  uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 16);  // [9][64] deposit tables
+  uint64_t* baseT = reinterpret_cast<uint64_t*>(red + 32);  // [9][64] deposit tables
   uint4* chk4 = reinterpret_cast<uint4*>(baseT + 9 * 64);   // the first kChunkSlots chunk records (4 x uint4 each)
   uint4* grp4 = chk4 + 4 * (kChunkSlots + 1);               // 3 x uint4 per group record
   uint4* bun4 = grp4 + 3 * (GCAP + 1);                      // 1 x uint4 per bundle record

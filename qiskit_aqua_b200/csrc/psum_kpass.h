@@ -21,4 +21,14 @@ PSUM_DECL_KPASS(4, 128)
 PSUM_DECL_KPASS(4, 256)
 #undef PSUM_DECL_KPASS
 
+// one entry point over the compiled (register bits, threads) configurations
+inline cudaError_t kpass_launch(int rb, int threads, int mode, int grid, size_t smem, cudaStream_t st, const double2* src,
+                                const double2* bra, double2* y, const PassParams& pp, double2* partial) {
+  if (rb == 4)
+    return threads == 256 ? kpass_launch_4_256(mode, grid, smem, st, src, bra, y, pp, partial)
+                          : kpass_launch_4_128(mode, grid, smem, st, src, bra, y, pp, partial);
+  return threads == 512 ? kpass_launch_3_512(mode, grid, smem, st, src, bra, y, pp, partial)
+                        : kpass_launch_3_256(mode, grid, smem, st, src, bra, y, pp, partial);
+}
+
 }  // namespace psum

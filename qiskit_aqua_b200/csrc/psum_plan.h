@@ -205,6 +205,7 @@ struct PlanOptions {
   int late_split = 0;  // 1: groups that touch ONE late qubit get passes that free only that late qubit, so
                        // their tiles complete chunk pair by chunk pair while the state arrives (run_ready)
   int reg_bits = 3;    // 3: 8 amplitudes per thread, 256-thread CTAs; 4: 16 per thread, 128-thread CTAs
+                       // (4 per thread at 64 registers and twice the warps was measured: 378 vs 305 ms on C4)
   int share_weight = 100;  // percent: weight of the partner-load term when the register qubits are chosen
   int min_bundle = 2;  // a bundle of fewer members, all of them fast, is split into singles (own loads,
                        // straight-line loops): sharing only pays when enough members use one load set
@@ -532,7 +533,8 @@ inline PassHost build_pass(const std::vector<CompTerm>& comp,
     }
     // quadratic group?  (all patterns real, at most two tile bits each)
     {
-      bool quad = (int)pats.size() >= kQuadMinPatterns && pats.size() <= 255 && quad_table_doubles(P.L, rb) <= caps.quad;
+      bool quad = (int)pats.size() >= kQuadMinPatterns && pats.size() <= 255 && quad_table_doubles(P.L, rb) <= caps.quad &&
+                  P.L - kRegBitLo - rb <= 5;   // a w table (2^nW entries) is filled by one warp, lane = index
       for (const PatTmp& pt : pats)
         if (pt.cls >= NA || __builtin_popcount(pt.zt) > 2) quad = false;
       if (quad) {
