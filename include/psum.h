@@ -51,7 +51,9 @@ int psum_create(int n_qubits, int64_t n_terms, const uint64_t* x_mask, const uin
 int psum_destroy(psum_handle_t h);
 
 /* Tuning/testing knobs (before first use): "tile_bits" (11..13), "low_bits" (1..8),
- * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover";
+ * "kernel" (0 auto, 1 streaming kernel A only, 2 tiled kernel B), "min_cover" (3: a pass is opened only
+ * for that many x-groups, fewer read their partners from global memory), "plan_tries" (64: randomised
+ * restarts of the pass planner, the plan with the least HBM traffic wins);
  * "reg_bits" (3 default | 4): amplitudes per thread = 2^reg_bits.  x-groups whose masks differ only
  * in the register qubits of a pass share one set of partner loads (a "bundle");
  * "cta_mode" (0 auto | 1 two CTAs per SM | 2 one big CTA per SM): a pass with quadratic groups or more

@@ -416,6 +416,20 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       if (STORE && P.accumulate && (tid & 7) == 0)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(y + idx));
     }
+    // the old y of the first round is loaded NOW, so that its latency hides behind the fold and the wait
+    // for the tile instead of stalling every warp of the CTA at once right after the barrier (real-only
+    // passes; with imaginary patterns the longer live range costs more than it hides: measured)
+    constexpr bool EARLY_Y = !IM;
+    double2 yacc[NA];
+    auto init_acc = [&](int rnd) {
+      const uint32_t t0 = (uint32_t)rnd * (NT * NA) + (uint32_t)warp * (32u * NA) + (uint32_t)lane;
+      const char* ybase = reinterpret_cast<const char*>(y + (base | offLane | offHi[t0 >> 7]));
+#pragma unroll
+      for (int r = 0; r < NA; ++r)
+        yacc[r] = (STORE && P.accumulate) ? *reinterpret_cast<const double2*>(ybase + P.roff[r])
+                                          : make_double2(0.0, 0.0);
+    };
+    if (EARLY_Y) init_acc(0);
     if (one_chunk && bb == 0) {   // the fold overlaps the tile load; shared by the batch
       ChunkRec ch0;
       uint4* cw = reinterpret_cast<uint4*>(&ch0);
@@ -429,12 +443,7 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     for (int rnd = 0; rnd < nrounds; ++rnd) {
       const uint32_t t0 = (uint32_t)rnd * (NT * NA) + (uint32_t)warp * (32u * NA) + (uint32_t)lane;
       const uint64_t i0 = base | offLane | offHi[t0 >> 7];   // register bits of t0 are clear
-      double2 yacc[NA];
-      const char* ybase = reinterpret_cast<const char*>(y + i0);
-#pragma unroll
-      for (int r = 0; r < NA; ++r)
-        yacc[r] = (STORE && P.accumulate) ? *reinterpret_cast<const double2*>(ybase + P.roff[r])
-                                          : make_double2(0.0, 0.0);
+      if (!EARLY_Y || rnd > 0) init_acc(rnd);
 
       for (int c = 0; c < P.nchunks; ++c) {
         // the chunk record always comes from shared memory (a global fallback inside this loop is

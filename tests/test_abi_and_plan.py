@@ -79,6 +79,22 @@ def test_plan_covers_every_group_once(tile_bits):
     assert info['n_passes'] < info['n_xgroups'] / 4               # tiling pays: few HBM sweeps
 
 
+def test_headline_plan_reaches_the_pair_covering_bound():
+    """The 30-qubit headline operator (bench.py, config C4) holds every XX/YY pair mask: all pairs of the 27
+    high qubits must share a free set of 9 high qubits, which needs >= ceil(27/9 * ceil(26/8)) = 12 passes
+    (Schoenheim bound).  The planner's randomised restarts reach it; on 8 ranks (33 qubits) the local part
+    plus the six exchanged parts take 24."""
+    import bench
+    n, x, z, y, c = bench.workload(30, 'c4')
+    info = PauliSumEngine(n, x, z, y, c).info()
+    assert info['n_xgroups'] == 466 and info['n_remote_groups'] == 0
+    assert info['n_passes'] == 12
+    n, x, z, y, c = bench.workload(33, 'c4')
+    eng = PauliSumEngine(n, x, z, y, c)
+    eng.shard(0, 8)
+    assert eng.info()['n_passes'] <= 24
+
+
 def test_small_operator_uses_streaming_plan():
     n, x, z, y, c = W.two_local_random(8, 40, seed=1)
     assert PauliSumEngine(n, x, z, y, c).info()['n_passes'] == 0
