@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument('--copy-threads', type=int, default=0)
     ap.add_argument('--min-bundle', type=int, default=0)
     ap.add_argument('--plan-tries', type=int, default=0)
+    ap.add_argument('--term-cache', type=int, default=-1)
     ap.add_argument('--min-cover', type=int, default=0)
     ap.add_argument('--share-weight', type=int, default=-1)
     ap.add_argument('--comm-sms', type=int, default=-1)
@@ -289,6 +290,8 @@ def main():
         opts['min_bundle'] = args.min_bundle
     if args.plan_tries:
         opts['plan_tries'] = args.plan_tries
+    if args.term_cache >= 0:
+        opts['term_cache'] = args.term_cache
     if args.min_cover:
         opts['min_cover'] = args.min_cover
     if args.share_weight >= 0:

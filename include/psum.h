@@ -58,6 +58,8 @@ int psum_destroy(psum_handle_t h);
  * in the register qubits of a pass share one set of partner loads (a "bundle");
  * "cta_mode" (0 auto | 1 two CTAs per SM | 2 one big CTA per SM): a pass with quadratic groups or more
  * than one chunk runs as one CTA per SM with twice the threads and large staging capacities;
+ * "term_cache" (1 default): one-chunk passes without imaginary patterns keep their component terms in shared
+ * memory when they fit, so the per-tile fold does not read them from L2;
  * "copy_threads" (0 auto): host threads that fill the pinned bounce ring for pageable input;
  * "herm_pairing" (1 default): psum_expect of a Hermitian operator evaluates each amplitude pair
  * (i, i^x) once and doubles it (the imaginary part of the result is then exactly the rounding

@@ -140,6 +140,7 @@ struct psum_handle_s {
   bool hermitian = true, diagonal = true;
   PlanOptions opt;
   int lanczos_probe = 2;  // 0 off, 1 on, 2 auto (on for <= 2^20 amplitudes per rank)
+  int term_cache = 1;     // one-chunk passes keep their component terms in shared memory when they fit
   int herm_pairing = 1;   // <psi|H|psi> of a Hermitian operator: evaluate pairs (i, i^x) once
   std::vector<PartHost> parts;
   bool planned = false;
@@ -296,6 +297,17 @@ static int upload_plan(psum_handle_s* h, const std::vector<PartHost>& parts, voi
         for (const ChunkRec& cr : ph.chunks) max_nq = std::max<int>(max_nq, cr.nq);
         dp.params.quad_cap = max_nq * quad_table_doubles(ph.L, ph.rb);
         dp.smem = pass_smem_bytes(ph.L, big_cfg, dp.params.quad_cap);
+        // a one-chunk pass keeps its component terms in shared memory when they fit beside the tile
+        // (two CTAs per SM: 113 KB each; one big CTA: 227 KB)
+        dp.params.term_cache = 0;
+        if (h->term_cache && ph.chunks.size() == 1 && !ph.term_val.empty() && !ph.has_im) {   // real-only kernels only
+          const size_t extra = 16 * ph.term_val.size();
+          const size_t limit = (size_t)(big_cfg ? 227 : 113) * 1024;
+          if (dp.smem + extra <= limit) {
+            dp.params.term_cache = (int)ph.term_val.size();
+            dp.smem += extra;
+          }
+        }
         int per_sm = (dp.smem > 113 * 1024 || big_cfg) ? 1 : 2;
         dp.grid = (int)std::min<uint64_t>(dp.params.ntiles, (uint64_t)h->num_sms * per_sm);
         pass_partials += dp.grid;
@@ -449,7 +461,8 @@ extern "C" int psum_set_option(psum_handle_t h, const char* key, int64_t value) 
     h->opt.late_bits = (int)value;
   } else if (k == "herm_pairing") {
     h->herm_pairing = value ? 1 : 0;
-    return PSUM_OK;
+  } else if (k == "term_cache") {
+    h->term_cache = value ? 1 : 0;   // shared-memory sizes are fixed when the plan is uploaded: fall through
   } else if (k == "profile_exchange") {
     h->profile_exchange = value ? 1 : 0;
     return PSUM_OK;
@@ -880,6 +893,7 @@ static int launch_pass_batch(psum_handle_s* h, const DevPart& D, const DevPass& 
   pp.accumulate = 0;
   pp.batch = nb;
   pp.batch_stride = stride;
+  pp.term_cache = 0;   // the batched launch sizes its own shared memory (per-warp accumulators instead)
   const bool herm = h->hermitian && h->herm_pairing && D.g == 0;
   const int mode = kModeExpect | (dp.has_im ? kModeIm : 0) | (herm ? kModeHerm : 0);
   const bool big_cfg = (dp.threads << dp.rb) >= 4096;

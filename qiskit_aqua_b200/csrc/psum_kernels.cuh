@@ -43,6 +43,9 @@ struct PassParams {
   int n_nonfree;
   int accumulate;
   int quad_cap;   // doubles of the quad-table arena behind the tile
+  int term_cache; // > 0: a one-chunk pass keeps its `term_cache` component terms (zb, val) in shared memory behind
+                  // the quad arena (copied once per CTA): the per-tile fold then reads them at shared-memory
+                  // latency instead of ~L2 latency
   int batch;      // > 1: `batch` source vectors (stride batch_stride amplitudes) share the staged plan of each
                   // tile: the fold and the table build run once per tile, not once per state
                   // (expectation-only launches of one-chunk passes; partial[b * gridDim.x + block])
@@ -64,9 +67,10 @@ __host__ __device__ constexpr size_t pass_static_bytes_c(bool big) {
   return 8 * 64 + 16 * 32 + 8 * 9 * 64 + sizeof(ChunkRec) * (kChunkSlots + 1) + sizeof(GroupRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) +
          sizeof(BundleRec) * ((big ? kGrpCapBig : kGrpCapSmall) + 1) + sizeof(PatRec) * (big ? kPatCapBig : kPatCapSmall);
 }
-__host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap, int batch = 1) {
+__host__ __device__ constexpr size_t pass_smem_bytes_c(int L, bool big, int quad_cap, int batch = 1, int term_cache = 0) {
   return pass_static_bytes_c(big) + ((size_t)16 << L) + 8 * (size_t)quad_cap +
-         (batch > 1 ? (size_t)16 * 32 * kMaxBatch : 0);   // [warp][state] expectation accumulators (<= 32 warps)
+         (batch > 1 ? (size_t)16 * 32 * kMaxBatch : 0) +   // [warp][state] expectation accumulators (<= 32 warps)
+         (size_t)16 * (size_t)term_cache;                  // cached component terms: zb[term_cache], val[term_cache]
 }
 
 __device__ __forceinline__ double flip_sign(double v, int s) {
@@ -83,6 +87,11 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ double2 lds_d2(uint32_t a) {
@@ -234,6 +243,10 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
   double* qtab = reinterpret_cast<double*>(tile + tile_amps);   // tables of the chunk's quadratic groups
   double2* wacc = reinterpret_cast<double2*>(qtab + P.quad_cap);   // [warp][kMaxBatch], batched launches only
   const int nbatch = (!STORE && EXPECT && P.batch > 1) ? P.batch : 1;
+  // the shared-memory term cache is compiled into the real-only variants (the host enables it only for
+  // passes without imaginary patterns): in the IM variants the second fold path costs registers the
+  // round loops need (measured: C5 +2 %)
+  constexpr bool TCACHE = !IM;
   const uint4* pat4 = reinterpret_cast<const uint4*>(pat);
   const int nW = L - 5 - RB;                                 // warp/round tile bits
   const uint32_t tile_s = smem_addr(tile), grp_s = smem_addr(grp4), bun_s = smem_addr(bun4), pat_s = smem_addr(pat),
@@ -292,6 +305,10 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
     uint16_t* lq = reinterpret_cast<uint16_t*>(red) + 8;
     constexpr int kLongCap = 120;
     const bool has_long = (ch.q0 >> 31) != 0;
+    // term cache (optional, behind the quad arena and the batch accumulators): addresses derived here so
+    // that they do not occupy registers in the round loops
+    const uint32_t tc_zb_s = qtab_s + 8u * (uint32_t)P.quad_cap + (P.batch > 1 ? 16u * 32u * kMaxBatch : 0u);
+    const uint32_t tc_val_s = tc_zb_s + 8u * (uint32_t)P.term_cache;
     if (has_long && tid == 4) *lq_count = 0;
     if (copy_records || has_long) __syncthreads();
     auto put_pattern = [&](int p, int gp, double v) {
@@ -318,9 +335,17 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         }
       }
       double v = 0.0;
+      if (TCACHE && P.term_cache) {
 #pragma unroll 4
-      for (uint32_t t = ta; t < tb; ++t)
-        v += flip_sign(__ldg(P.term_val + t), __popcll(base & __ldg(P.term_zb + t)) & 1);
+        for (uint32_t t = ta; t < tb; ++t) {
+          const uint2 zb = lds_u2(tc_zb_s + 8u * t);
+          v += flip_sign(lds_d(tc_val_s + 8u * t), (__popc(zb.x & (uint32_t)base) + __popc(zb.y & (uint32_t)(base >> 32))) & 1);
+        }
+      } else {
+#pragma unroll 4
+        for (uint32_t t = ta; t < tb; ++t)
+          v += flip_sign(__ldg(P.term_val + t), __popcll(base & __ldg(P.term_zb + t)) & 1);
+      }
       put_pattern(p, gp, v);
     }
     if (has_long) {
@@ -330,8 +355,15 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
         const int p = (int)lq[li], gp = ch.p0 + p;
         const uint32_t ta = P.pat_tptr[gp], tb = P.pat_tptr[gp + 1];
         double v = 0.0;
-        for (uint32_t t = ta + (uint32_t)lane; t < tb; t += 32u)
-          v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+        if (TCACHE && P.term_cache) {
+          for (uint32_t t = ta + (uint32_t)lane; t < tb; t += 32u) {
+            const uint2 zb = lds_u2(tc_zb_s + 8u * t);
+            v += flip_sign(lds_d(tc_val_s + 8u * t), (__popc(zb.x & (uint32_t)base) + __popc(zb.y & (uint32_t)(base >> 32))) & 1);
+          }
+        } else {
+          for (uint32_t t = ta + (uint32_t)lane; t < tb; t += 32u)
+            v += flip_sign(P.term_val[t], __popcll(base & P.term_zb[t]) & 1);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) put_pattern(p, gp, v);
@@ -397,6 +429,14 @@ k_pass(const double2* __restrict__ src, const double2* __restrict__ bra, double2
       bun4[b] = reinterpret_cast<const uint4*>(P.bundles + ch0.b0)[b];
     if (tid < 3) grp4[ch0.ng * 3 + tid] = make_uint4(0u, 0u, 0u, 0u);   // read-ahead slots
     if (tid == 3) bun4[ch0.nb] = make_uint4(0u, 0u, 0u, 0u);
+    if (TCACHE) {
+      uint64_t* tc_zb = reinterpret_cast<uint64_t*>(wacc + (P.batch > 1 ? 32 * kMaxBatch : 0));
+      double* tc_val = reinterpret_cast<double*>(tc_zb + P.term_cache);
+      for (int t = tid; t < P.term_cache; t += NT) {
+        tc_zb[t] = P.term_zb[t];
+        tc_val[t] = P.term_val[t];
+      }
+    }
     // (made visible by the barrier at the top of the first tile)
   }
 

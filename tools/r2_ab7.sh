@@ -1,0 +1,7 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_reference_run.py tests/test_gpu_shim.py -m gpu -x -q > gpurun_out/ab7_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/ab7_pytest.log
+ms() { python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('RESULT $1', d['config']['workload'][:8], d['config']['qubits'], 'ms', round(d['ms_per_step'],2), 'passes', d['config']['passes'], 'parity', d.get('parity',{}).get('ok'))"; }
+for tc in 0 1; do
+  python bench.py --term-cache $tc --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>>gpurun_out/ab7_err.log | tee -a gpurun_out/ab7_lines.json | ms term_cache_$tc
+  python bench.py --term-cache $tc --workload c5 --qubits 28 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-parity 2>>gpurun_out/ab7_err.log | tee -a gpurun_out/ab7_lines.json | ms term_cache_$tc
+done
