@@ -52,6 +52,15 @@ def test_two_local_tiled(tile_bits, low_bits, reg_bits):
     assert info['n_bundles'] < info['n_group_records']        # partner loads are shared
 
 
+@pytest.mark.parametrize('term_cache', [0, 1])
+@pytest.mark.parametrize('cta_mode', [0, 1])
+def test_term_cache_on_and_off(term_cache, cta_mode):
+    """One-chunk real-only passes keep their component terms in shared memory (option term_cache, default
+    on); both settings give the oracle's H.psi and <H>, as one big CTA per SM and as two CTAs per SM."""
+    n, x, z, y, c = W.ising_heisenberg(18, n_triples=3000, seed=30)
+    _check(n, x, z, y, c, {'term_cache': term_cache, 'cta_mode': cta_mode})
+
+
 @pytest.mark.parametrize('cta_mode', [0, 1, 2])
 @pytest.mark.parametrize('reg_bits', [3, 4])
 @pytest.mark.parametrize('kind', ['c4', 'c5', 'molecular'])
