@@ -17,6 +17,10 @@
 // partner amplitudes are loaded ONCE per bundle and every member applies its own compile-time
 // register permutation pv[r ^ xr] -- the shared-memory pipe, which bounds this kernel, sees one
 // load set per bundle instead of one per group.
+// Per-tile overhead: a pass whose records fit one staging chunk copies its group / bundle records -- and,
+// for real-only passes, its component terms -- to shared memory ONCE per CTA; per tile only the fold
+// (signs of the bits outside S -> coefficients) and the quadratic-group tables are redone, overlapped with
+// the cp.async tile load; the old y of the first round is requested before the wait for the tile.
 // Kernel A (k_stream) is the plain streaming form used for n_loc < 11 qubits.
 #pragma once
 #include <cuda_runtime.h>
