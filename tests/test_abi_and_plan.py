@@ -58,6 +58,27 @@ def test_invalid_arguments():
         eng.set_option('no_such_option', 1)
     with pytest.raises(PsumError):
         eng.shard(0, 3)                                                         # not a power of 2
+    with pytest.raises(PsumError):
+        eng.set_option('plan_tries', 0)
+    with pytest.raises(PsumError):
+        eng.set_option('reg_bits', 2)
+    eng.set_option('term_cache', 0)
+    eng.set_option('plan_tries', 8)
+
+
+def test_planner_restarts_only_ever_lower_the_cost():
+    """More randomised restarts never give a plan with more HBM sweeps (the cheapest plan wins), and the
+    kernel-side options do not change the plan."""
+    n, x, z, y, c = W.ising_heisenberg(24, n_triples=2000, seed=7)
+    counts = []
+    for tries in (1, 8, 64):
+        eng = PauliSumEngine(n, x, z, y, c, {'plan_tries': tries})
+        info = eng.info()
+        counts.append(3 * info['n_passes'] + info['n_remote_groups'])
+    assert counts[0] >= counts[1] >= counts[2]
+    a = PauliSumEngine(n, x, z, y, c, {'term_cache': 0}).info()
+    b = PauliSumEngine(n, x, z, y, c, {'term_cache': 1}).info()
+    assert a == b
 
 
 @pytest.mark.parametrize('tile_bits', [11, 12, 13])
