@@ -834,8 +834,14 @@ inline std::vector<PartHost> build_parts(const std::vector<MergedTerm>& terms, i
       // y (3 units), a remote group re-reads one partner vector (1 unit)
       std::vector<PassChoice> pcs;
       long best_cost = -1;
+      // the restarts share a deterministic work budget (mask visits of the greedy loops), so that an
+      // operator with tens of thousands of distinct x-masks is still planned in about a second
+      double work = 0.0;
+      constexpr double kPlanWorkBudget = 4e8;
       for (int t = 0; t < std::max(1, opt.plan_tries); ++t) {
+        if (t >= 4 && work > kPlanWorkBudget) break;
         std::vector<PassChoice> cand = choose_passes(masks, n_loc, L, opt.low_bits, opt.min_cover, (uint64_t)t, opt.late_bits, opt.late_split);
+        work += (double)masks.size() * (double)cand.size() * (double)std::max(1, L - opt.low_bits);
         long n_remote = 0;
         for (auto& pc : cand)
           for (int mi : pc.members)
