@@ -1375,7 +1375,6 @@ static int ensure_host_plan(psum_handle_s* h, int late) {
   // block of partials: grow the partial buffer when a large plan needs more than upload() reserved
   size_t need_h = 0;
   const size_t nchunks = (size_t)1 << late;
-  const int cbits = h->n_loc - late;
   for (const DevPart& D : h->dparts_h) {
     need_h += (size_t)D.grid_stream;
     for (const DevPass& dp : D.passes) need_h += (size_t)dp.grid * nchunks;   // upper bound: one block per tile range
