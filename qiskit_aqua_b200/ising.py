@@ -83,22 +83,20 @@ def random_graph(n, weight_range=10, edge_prob=0.3, negative_weight=True, savefi
         aqua_globals.random_seed = seed
     rng = aqua_globals.random
     w = np.zeros((n, n))
-    m = 0
-    for i in range(n):
-        for j in range(i + 1, n):
-            if rng.random() <= edge_prob:
-                w[i, j] = rng.integers(1, weight_range)
-                if rng.random() >= 0.5 and negative_weight:
-                    w[i, j] *= -1
-                m += 1
+    # the three draws of an edge are conditional on each other, so the pairs are visited one by one in
+    # the reference's order (row-major upper triangle); everything after the draws is array code
+    for i, j in zip(*np.triu_indices(n, k=1)):
+        if rng.random() > edge_prob:
+            continue
+        weight = rng.integers(1, weight_range)
+        w[i, j] = -weight if (rng.random() >= 0.5 and negative_weight) else weight
+    rows, cols = np.nonzero(w)                      # the edges (weights are >= 1): upper triangle, row-major
     w += w.T
     if savefile:
-        with open(savefile, 'w', encoding='utf8') as f:
-            f.write('{} {}\n'.format(n, m))
-            for i in range(n):
-                for j in range(i + 1, n):
-                    if w[i, j] != 0:
-                        f.write('{} {} {}\n'.format(i + 1, j + 1, w[i, j]))
+        lines = ['%d %d\n' % (n, len(rows))]
+        lines += ['%d %d %s\n' % (a + 1, b + 1, w[a, b]) for a, b in zip(rows, cols)]
+        with open(savefile, 'w', encoding='utf8') as handle:
+            handle.writelines(lines)
     return w
 
 
